@@ -1,0 +1,51 @@
+// api.cu — implementation selection for the MLP entry points of the C ABI.
+// impl 0 = CUDA-core twin (mlp.cu), impl 1 = tcgen05/TMEM kernels (mlp_tc.cu).  The default is the
+// tensor-core path; F2B_MLP_IMPL=0 in the environment (or f2b_set_mlp_impl) selects the twin.
+#include "common.cuh"
+#include <stdlib.h>
+
+extern "C" int f2b_mlp_fwd_v0(const void*, const void*, int, int, void*, void*, void*);
+extern "C" int f2b_mlp_bwd_v0(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
+#ifdef F2B_HAVE_TC
+extern "C" int f2b_mlp_fwd_tc(const void*, const void*, int, int, void*, void*, void*);
+extern "C" int f2b_mlp_bwd_tc(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
+#endif
+
+static int g_mlp_impl = -1;
+static int mlp_impl() {
+  if (g_mlp_impl < 0) {
+    const char* e = getenv("F2B_MLP_IMPL");
+#ifdef F2B_HAVE_TC
+    g_mlp_impl = e ? atoi(e) : 1;
+#else
+    g_mlp_impl = 0;
+    (void)e;
+#endif
+  }
+  return g_mlp_impl;
+}
+
+extern "C" int f2b_set_mlp_impl(int impl) {
+#ifndef F2B_HAVE_TC
+  if (impl != 0) { f2b::set_error("f2b_set_mlp_impl: tcgen05 path not built"); return F2B_EUNSUPPORTED; }
+#endif
+  g_mlp_impl = impl;
+  return F2B_OK;
+}
+extern "C" int f2b_get_mlp_impl(void) { return mlp_impl(); }
+
+extern "C" int f2b_mlp_fwd(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                           void* out_f16, void* hidden_save_f16, void* stream) {
+#ifdef F2B_HAVE_TC
+  if (mlp_impl() == 1) return f2b_mlp_fwd_tc(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f16, hidden_save_f16, stream);
+#endif
+  return f2b_mlp_fwd_v0(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f16, hidden_save_f16, stream);
+}
+extern "C" int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                           const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                           float* dparams_f32, void* stream) {
+#ifdef F2B_HAVE_TC
+  if (mlp_impl() == 1) return f2b_mlp_bwd_tc(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
+#endif
+  return f2b_mlp_bwd_v0(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
+}

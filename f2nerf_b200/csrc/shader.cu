@@ -1,0 +1,219 @@
+// shader.cu — SH view-direction encode, shader-MLP input assembly (constant-1 channel, appearance
+// embedding) and the scaled-sigmoid colour activation, fused around the MLP.
+//
+// Replaces SHKenerl (src/Shader/SHShader.cu:10-106, degree <= 4 used by every shipped config),
+// the torch::cat / ones_like / ScatterIdx / ScatterAdd chain of Renderer::Render
+// (src/Renderer/Renderer.cpp:179-187, src/Utils/CustomOps/Scatter.cu:10-40,110-120),
+// tiny-cuda-nn's identity encoding cast (encodings/identity.h:45-85) and the sigmoid of
+// SHShader::Query (src/Shader/SHShader.cpp:27-28).
+#include "common.cuh"
+
+namespace f2b {
+
+// degree-4 real spherical harmonics in tiny-cuda-nn ordering (SHShader.cu:32-50)
+__device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void sh_encode_kernel(const float* __restrict__ dirs, int n, int degree, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float o[16];
+  sh4(dirs[size_t(i) * 3], dirs[size_t(i) * 3 + 1], dirs[size_t(i) * 3 + 2], o);
+  const int m = degree * degree;
+  for (int k = 0; k < m; k++) out[size_t(i) * m + k] = o[k];
+}
+
+// ScatterIdxKernal (Scatter.cu:110-120): ray -> sample broadcast of the camera index, warp per ray.
+__global__ void scatter_idx_kernel(int n_rays, const int* __restrict__ bounds, const int* __restrict__ emb_idx,
+                                   int* __restrict__ out) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= n_rays) return;
+  const int v = emb_idx[ray];
+  for (int i = bounds[2 * ray] + lane; i < bounds[2 * ray + 1]; i += 32) out[i] = v;
+}
+
+// mlp_in[p] = fp16([1, feat[1..15]] + app_emb[cam(p)] | SH4(dir_p))
+__global__ void __launch_bounds__(128)
+shader_prep_kernel(const float* __restrict__ scene_feat, const float* __restrict__ dirs,
+                   const float* __restrict__ app_emb, const int* __restrict__ pt_emb_idx, int n,
+                   __half* __restrict__ mlp_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v[32];
+  const float4* f4 = reinterpret_cast<const float4*>(scene_feat + size_t(i) * 16);
+#pragma unroll
+  for (int q = 0; q < 4; q++) { const float4 a = __ldg(f4 + q); v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w; }
+  v[0] = 1.f;
+  if (app_emb) {
+    const float4* e4 = reinterpret_cast<const float4*>(app_emb + size_t(pt_emb_idx[i]) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 a = __ldg(e4 + q);
+      v[4 * q] = fadd(v[4 * q], a.x); v[4 * q + 1] = fadd(v[4 * q + 1], a.y);
+      v[4 * q + 2] = fadd(v[4 * q + 2], a.z); v[4 * q + 3] = fadd(v[4 * q + 3], a.w);
+    }
+  }
+  sh4(__ldg(dirs + size_t(i) * 3), __ldg(dirs + size_t(i) * 3 + 1), __ldg(dirs + size_t(i) * 3 + 2), v + 16);
+  uint4* dst = reinterpret_cast<uint4*>(mlp_in + size_t(i) * 32);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    __half2 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(v[8 * q + 2 * k], v[8 * q + 2 * k + 1]);
+    dst[q] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// rgb = (1 + 2e-3) / (1 + exp(-o)) - 1e-3 on the fp16 MLP output (SHShader.cpp:27-28)
+__global__ void shader_act_kernel(const __half* __restrict__ raw, int n, float* __restrict__ rgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float eps = 1e-3f;
+  const float c = 1.f + 2.f * eps;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float o = __half2float(raw[size_t(i) * 16 + k]);
+    rgb[size_t(i) * 3 + k] = fsub(fdiv(c, fadd(1.f, expf(-o))), eps);
+  }
+}
+
+// dL/d raw_out (fp16, times loss_scale) from dL/d rgb; channels 3..15 get zero.
+__global__ void shader_act_bwd_kernel(const __half* __restrict__ raw, const float* __restrict__ d_rgb, int n,
+                                      float loss_scale, __half* __restrict__ d_raw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c = 1.f + 2.f * 1e-3f;
+  __half2 h[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) h[k] = __floats2half2_rn(0.f, 0.f);
+  float g[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float o = __half2float(raw[size_t(i) * 16 + k]);
+    const float s = 1.f / (1.f + expf(-o));
+    g[k] = d_rgb[size_t(i) * 3 + k] * c * s * (1.f - s) * loss_scale;
+  }
+  h[0] = __floats2half2_rn(g[0], g[1]);
+  h[1] = __floats2half2_rn(g[2], 0.f);
+  uint4* dst = reinterpret_cast<uint4*>(d_raw + size_t(i) * 16);
+  dst[0] = *reinterpret_cast<uint4*>(h);
+  dst[1] = *reinterpret_cast<uint4*>(h + 4);
+}
+
+// Backward of the input assembly: d scene_feat[:,1:16] = d mlp_in[:,1:16] / loss_scale (channel 0 of
+// scene_feat is the density logit, filled by the composite backward), and the appearance-embedding
+// gradient d app_emb[cam] += d mlp_in[:,0:16] (ScatterAddFuncBackwardBlock, Scatter.cu:23-40) via a
+// block-local shared-memory histogram followed by one atomicAdd per (camera, channel) per block.
+__global__ void __launch_bounds__(256)
+shader_prep_bwd_kernel(const __half* __restrict__ d_mlp_in, const int* __restrict__ pt_emb_idx, int n,
+                       float inv_loss_scale, int n_emb, float* __restrict__ d_scene_feat,
+                       float* __restrict__ d_app_emb) {
+  extern __shared__ float s_emb[];   // [n_emb][16] when d_app_emb
+  if (d_app_emb) {
+    for (int k = threadIdx.x; k < n_emb * 16; k += blockDim.x) s_emb[k] = 0.f;
+    __syncthreads();
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + blockDim.x - 1) / blockDim.x) * blockDim.x;
+       i += gridDim.x * blockDim.x) {
+    if (i < n) {
+      const uint4* s = reinterpret_cast<const uint4*>(d_mlp_in + size_t(i) * 32);
+      float g[16];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint4 r = s[q];
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); g[8 * q + 2 * k] = f.x * inv_loss_scale; g[8 * q + 2 * k + 1] = f.y * inv_loss_scale; }
+      }
+      float* dst = d_scene_feat + size_t(i) * 16;
+#pragma unroll
+      for (int k = 1; k < 16; k++) dst[k] = g[k];
+      if (d_app_emb) {
+        float* e = s_emb + pt_emb_idx[i] * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++) atomicAdd(e + k, g[k]);
+      }
+    }
+  }
+  if (d_app_emb) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_emb * 16; k += blockDim.x) {
+      const float v = s_emb[k];
+      if (v != 0.f) atomicAdd(d_app_emb + k, v);
+    }
+  }
+}
+
+}  // namespace f2b
+
+using namespace f2b;
+
+extern "C" int f2b_sh_encode(const float* dirs, int n_pts, int degree, float* out, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  if (degree < 1 || degree > 4) { set_error("f2b_sh_encode: degree %d unsupported (1..4)", degree); return F2B_EUNSUPPORTED; }
+  sh_encode_kernel<<<div_up(n_pts, 256), 256, 0, as_stream(stream)>>>(dirs, n_pts, degree, out);
+  return check_launch("f2b_sh_encode");
+}
+
+extern "C" int f2b_scatter_idx(const int* pts_idx_bounds, const int* emb_idx, int n_rays, int* out, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  scatter_idx_kernel<<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(n_rays, pts_idx_bounds, emb_idx, out);
+  return check_launch("f2b_scatter_idx");
+}
+
+extern "C" int f2b_shader_prep(const float* scene_feat, const float* dirs, const float* app_emb,
+                               const int* pt_emb_idx, int n_pts, void* mlp_in_f16, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(scene_feat && dirs && mlp_in_f16, "f2b_shader_prep: null pointer");
+  F2B_REQUIRE(!app_emb || pt_emb_idx, "f2b_shader_prep: app_emb without pt_emb_idx");
+  shader_prep_kernel<<<div_up(n_pts, 128), 128, 0, as_stream(stream)>>>(scene_feat, dirs, app_emb, pt_emb_idx, n_pts,
+                                                                       (__half*)mlp_in_f16);
+  return check_launch("f2b_shader_prep");
+}
+
+extern "C" int f2b_shader_act(const void* raw_out_f16, int n_pts, float* rgb, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  shader_act_kernel<<<div_up(n_pts, 256), 256, 0, as_stream(stream)>>>((const __half*)raw_out_f16, n_pts, rgb);
+  return check_launch("f2b_shader_act");
+}
+
+extern "C" int f2b_shader_act_bwd(const void* raw_out_f16, const float* d_rgb, int n_pts, float loss_scale,
+                                  void* d_raw_f16, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  shader_act_bwd_kernel<<<div_up(n_pts, 256), 256, 0, as_stream(stream)>>>((const __half*)raw_out_f16, d_rgb, n_pts,
+                                                                          loss_scale, (__half*)d_raw_f16);
+  return check_launch("f2b_shader_act_bwd");
+}
+
+extern "C" int f2b_shader_prep_bwd(const void* d_mlp_in_f16, const int* pt_emb_idx, int n_pts, float inv_loss_scale,
+                                   int n_emb, float* d_scene_feat, float* d_app_emb, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(d_mlp_in_f16 && d_scene_feat, "f2b_shader_prep_bwd: null pointer");
+  F2B_REQUIRE(!d_app_emb || (pt_emb_idx && n_emb > 0 && n_emb * 16 * 4 <= 96 * 1024), "f2b_shader_prep_bwd: bad embedding args");
+  int sms = 148;
+  f2b_device_info(&sms, nullptr);
+  const int blocks = d_app_emb ? min(div_up(n_pts, 256), sms * 4) : div_up(n_pts, 256);
+  const size_t smem = d_app_emb ? size_t(n_emb) * 16 * sizeof(float) : 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(shader_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  shader_prep_bwd_kernel<<<blocks, 256, smem, as_stream(stream)>>>((const __half*)d_mlp_in_f16, pt_emb_idx, n_pts,
+                                                                  inv_loss_scale, n_emb, d_scene_feat, d_app_emb);
+  return check_launch("f2b_shader_prep_bwd");
+}

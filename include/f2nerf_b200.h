@@ -1,0 +1,183 @@
+/* f2nerf_b200.h — C ABI of the B200-native (sm_100a) F2-NeRF per-ray rendering hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + a cudaStream_t (as void*), never
+ * allocates, never retains a pointer past the call, never throws.  Return value: 0 on success,
+ * negative F2B_E* on error (message via f2b_last_error()).  No torch types cross this boundary.
+ *
+ * Each function names the reference interface (file:line under Totoro97/f2-nerf @98f0daa) it
+ * replaces.  Byte layouts of the octree blobs are the reference's own (PersSampler.h:15-37):
+ *   TreeNode  64 B : center f32x3 @0, side_len f32 @12, parent i32 @16, childs i32x8 @20,
+ *                    is_leaf u8 @52, trans_idx i32 @56
+ *   TransInfo 544 B: w2xz[12] row-major 2x4 f32 @0, weight row-major 3x12 f32 @384,
+ *                    center f32x3 @528, dis_summary f32 @540
+ *   EdgePool  64 B : t_idx_a i32 @0, t_idx_b i32 @4, center f32x3 @8, dir_0 f32x3 @20, dir_1 f32x3 @32
+ */
+#ifndef F2NERF_B200_H
+#define F2NERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F2B_OK            0
+#define F2B_EINVAL      (-1)
+#define F2B_ECUDA       (-2)
+#define F2B_EUNSUPPORTED (-3)
+
+#define F2B_N_LEVELS    16
+#define F2B_N_CHANNELS   2
+#define F2B_N_PROS      12
+#define F2B_MAX_SAMPLE_PER_RAY 1024
+#define F2B_MLP_WIDTH   64
+#define F2B_MLP_IN      32
+#define F2B_MLP_OUT_PAD 16
+
+const char* f2b_last_error(void);
+int  f2b_abi_version(void);
+/* SM count / L2 bytes of the current device (grid sizing, bench reporting). */
+int  f2b_device_info(int* sm_count, int* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler  — replaces PersSampler::GetSamples (src/PtsSampler/PersSampler.cu:317-434):
+ * FindRayOctreeIntersectionKernel<false/true> (:53-152) + RayMarchKernel<false/true> (:189-314)
+ * are fused into one traverse-and-march kernel run twice (count, fill); the host syncs once
+ * (to size the outputs) instead of twice, and no hit list is materialised in HBM.
+ * rays_d must already be unit length (the reference normalises with ATen at :319).
+ * rays_noise has F2B_MAX_SAMPLE_PER_RAY + n_rays + 10 floats, already scaled by fineness (:373-381).
+ * ------------------------------------------------------------------------------------------ */
+/* Pass 1: per-ray sample counts -> exclusive/inclusive bounds (reference: cumsum at :395),
+ * totals[0] = n_all_pts, totals[1] = n_all_oct_intersect (for the sampled_oct_per_ray EMA, :378). */
+int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                      const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                      float near, float far, float sample_l, int scale_by_dis,
+                      int max_oct_intersect_per_ray,
+                      int* ray_counts /* [n_rays] caller-owned scratch */,
+                      int* pts_idx_bounds /* [n_rays,2] out */, int* totals /* [2] out */,
+                      void* stream);
+/* Pass 2: emit samples.  anchors is [P,3] i32: [:,0]=trans_idx, [:,1]=node idx, [:,2]=0
+ * (the reference leaves [:,2] uninitialised, PersSampler.cu:284-285). */
+int f2b_sampler_fill(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                     const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                     float near, float far, float sample_l, int scale_by_dis,
+                     int max_oct_intersect_per_ray, const int* pts_idx_bounds,
+                     float* pts /* [P,3] warped */, float* dirs /* [P,3] */, float* dt /* [P] */,
+                     float* t /* [P] */, int* anchors /* [P,3] */, float* first_oct_dis /* [n_rays] */,
+                     void* stream);
+/* GetEdgeSamplesKernel (PersSampler.cu:436-452). */
+int f2b_edge_samples(const void* edge_pool, const void* trans, const int* edge_idx,
+                     const float* edge_coord /* [n,2] */, int n_pts,
+                     float* out_pts /* [n,2,3] */, int* out_idx /* [n,2] */, void* stream);
+/* MarkVistNodeKernel (PersSampler.cu:475-526). oct_idx has element stride oct_stride (3 for anchors[:,1]). */
+int f2b_oct_mark_visit(const int* pts_idx_bounds, int n_rays, const int* oct_idx, int oct_stride,
+                       const float* weights, const float* alphas,
+                       int* vote_weight, int* vote_alpha, int* visit_mark, int* visit_cnt,
+                       void* stream);
+/* The ATen stat update + MarkInvalidNodes (PersSampler.cu:579-603) in one kernel. */
+int f2b_oct_update_stats(const int* vote_weight, const int* vote_alpha, const int* visit_mark,
+                         int* weight_stats, int* alpha_stats, void* tree_nodes, int n_nodes,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Field — replaces Hash3DAnchored::AnchoredQuery (src/Field/Hash3DAnchored.cpp:84-99),
+ * Hash3DAnchoredFunction::forward/backward (Hash3DAnchored.cu:160-233) and TCNNWP::Query
+ * (TCNNWP.cpp:102-243, tiny-cuda-nn FullyFusedMLP<half,64>).
+ * table_f16: the fp16 shadow of feat_pool_ ([pool_size,2] halves); level l starts at half
+ * element l*local_size (the reference's overlapping-level quirk, Hash3DAnchored.cu:37).
+ * ------------------------------------------------------------------------------------------ */
+/* The 16 per-level scales exp2f(7*l/15+3) exactly as the device computes them
+ * (Hash3DAnchored.cu:29; MUFU.EX2 is not reproducible on a CPU, so the oracle takes these). */
+int f2b_hash_level_scales(float* scales16_host);
+/* fp32 master table -> fp16 shadow (Hash3DAnchored.cu:186 does this on every call). */
+int f2b_table_to_half(const float* table_f32, void* table_f16, int64_t n, void* stream);
+/* Encode: pts are the sampler's warped coordinates (the (p+1)/2 of Hash3DAnchored.cpp:91 is fused).
+ * vol = anchors[:,0] with element stride vol_stride.  out: [P,32] fp16 (level-major, 2 ch). */
+int f2b_hash_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool,
+                 int n_volumes, int local_size,
+                 const float* pts, const int* vol, int vol_stride, int n_pts,
+                 void* out_f16, void* stream);
+/* Backward: grad_feat [P,32] (fp16 when grad_is_f16, else fp32; dL/d encoded features), each value
+ * multiplied by grad_mul (e.g. 1/loss_scale), scattered into grad_table [pool_size,2] fp32 (zeroed by
+ * the caller) with red.global.add.v2.f32 — instead of the reference's fp16 atomicAdd(__half2) of
+ * grad*128 and a later /128 (Hash3DAnchored.cu:81-155,199-233). */
+int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
+                 const float* pts, const int* vol, int vol_stride, int n_pts,
+                 const void* grad_feat, int grad_is_f16, float grad_mul,
+                 float* grad_table, void* stream);
+
+/* MLP (no biases, ReLU hidden, linear out padded to 16): params_f16 = [W0 64xin | (W_h 64x64)*n_hidden_matmuls | W_out 16x64],
+ * each row-major [out][in] (fully_fused_mlp.cu:654-677).  in: [P,32] fp16.  out: [P,16] fp16.
+ * hidden_save: nullable, [(n_hidden_matmuls+1), P, 64] fp16 forward activations for backward. */
+int f2b_mlp_fwd(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                void* out_f16, void* hidden_save_f16, void* stream);
+/* Backward: dL/dout [P,16] fp16 (already multiplied by loss_scale) -> dL/din [P,32] fp16 (nullable),
+ * dL/dparams fp32 (same layout as params, accumulated in fp32; caller zeroes), both still scaled. */
+int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                const void* params_f16, int n_hidden_matmuls, int n_pts,
+                void* din_f16, float* dparams_f32, void* stream);
+/* fp32 -> fp16 elementwise with optional scale (identity encoding / loss-scale casts, TCNNWP.cpp:111,168). */
+int f2b_cast_f32_to_f16(const float* src, void* dst, int64_t n, float scale, void* stream);
+int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
+
+/* Fused field forward: hash encode + MLP(32->64->16), encoded features never touch HBM unless
+ * feat_save is given (backward needs them).  out: [P,16] fp32 (fp16-rounded values, as TCNNWP::Query). */
+int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool,
+                  int n_volumes, int local_size, const void* mlp_params_f16,
+                  const float* pts, const int* vol, int vol_stride, int n_pts,
+                  float* out_f32, void* feat_save_f16, void* hidden_save_f16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Shader — replaces SHShader::Query (src/Shader/SHShader.cpp:23-29, SHShader.cu:10-118).
+ * ------------------------------------------------------------------------------------------ */
+int f2b_sh_encode(const float* dirs, int n_pts, int degree, float* out, void* stream);
+/* Fused: in = [shading_feat(16) | SH4(dir)(16)] -> fp16 -> MLP(32->64->64->16) -> rgb = 1.002*sigmoid(o)-0.001.
+ * mlp_in_save [P,32] fp16, hidden_save [2,P,64] fp16, raw_out_save [P,16] fp16: nullable (for backward). */
+int f2b_shader_fwd(const float* shading_feat /* [P,16] */, const float* dirs /* [P,3] */,
+                   const void* mlp_params_f16, int n_pts, float* rgb /* [P,3] */,
+                   void* mlp_in_save_f16, void* hidden_save_f16, void* raw_out_save_f16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Composite — replaces the Renderer::Render tail (src/Renderer/Renderer.cpp:107-150,196-208),
+ * FlexOps::{Sum,AccumulateSum} (src/Utils/CustomOps/FlexOps.cu), TruncExp (CustomOps.cpp:9-18),
+ * FilterIdxBounds/CountValidPts (Renderer.cu:8-50) and the gather-compaction (Renderer.cpp:126-132).
+ * All per-ray sums run in the reference's serial left-to-right order (bit-compatible rounding).
+ * ------------------------------------------------------------------------------------------ */
+/* No-grad early-stop pass: density logit (scene_feat[:,0], element stride logit_stride) + dt ->
+ * weights, alphas (for UpdateOctNodes), keep mask (trans > 1e-4) and the compacted bounds. */
+int f2b_early_stop(const float* logit, int logit_stride, const float* dt, const int* pts_idx_bounds,
+                   int n_rays, float* weights, float* alphas, uint8_t* keep,
+                   int* ray_counts /* [n_rays] caller-owned scratch */,
+                   int* new_bounds /* [n_rays,2] */, int* total_kept /* [1] */, void* stream);
+/* Gather-compact the surviving samples (44 B/pt). */
+int f2b_compact_samples(const uint8_t* keep, const int* old_bounds, const int* new_bounds, int n_rays,
+                        const float* pts, const float* dirs, const float* dt, const float* t,
+                        const int* anchors,
+                        float* pts_o, float* dirs_o, float* dt_o, float* t_o, int* anchors_o,
+                        void* stream);
+/* Forward composite. logit: scene_feat[:,0] (stride logit_stride); rgb [P,3]; t is the raw sample t
+ * (the +1e-2 of Renderer.cpp:197 is applied inside).  Outputs per ray: colors[3], disparity, depth;
+ * per point: weights. */
+int f2b_composite_fwd(const float* logit, int logit_stride, const float* rgb, const float* dt,
+                      const float* t, const int* pts_idx_bounds, const float* bg_color, int n_rays,
+                      float* colors, float* disparity, float* depth, float* weights, void* stream);
+/* Backward of the above (+ TruncExp backward + optional GradientScaling, CustomOps.cu:68-80):
+ * given dL/dcolors [R,3], dL/ddisparity [R], dL/ddepth [R] (nullable), dL/dweights [P] (nullable)
+ * -> dL/dlogit [P] (written with stride dlogit_stride), dL/drgb [P,3].
+ * grad_scaling_progress >= 1 disables gradient scaling. */
+int f2b_composite_bwd(const float* logit, int logit_stride, const float* rgb, const float* dt,
+                      const float* t, const int* pts_idx_bounds, const float* bg_color, int n_rays,
+                      const float* d_colors, const float* d_disparity, const float* d_depth,
+                      const float* d_weights, float grad_scaling_progress,
+                      float* d_logit, int dlogit_stride, float* d_rgb, void* stream);
+/* Stand-alone FlexOps (FlexOps.h:15-16) for callers that use them directly. */
+int f2b_flex_sum(const float* val, int vec, const int* idx_start_end, int n_outs, float* sum, void* stream);
+int f2b_flex_accumulate_sum(const float* val, const int* idx_start_end, int n_outs, int include_this,
+                            float* out, void* stream);
+/* WeightVar loss forward/backward (CustomOps.cu:12-66). */
+int f2b_weight_var_fwd(const float* weights, const int* idx_start_end, int n_outs, float* out_vars, void* stream);
+int f2b_weight_var_bwd(const float* weights, const int* idx_start_end, int n_outs, const float* dl_dvars,
+                       float* dl_dw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F2NERF_B200_H */
