@@ -1,0 +1,116 @@
+"""ctypes binding of the C ABI in include/f2nerf_b200.h (libf2nerf_b200.so, sm_100a only).
+
+The product path has no CPU fallback: if the shared library is missing or does not load, importing
+this module raises.  Tensors cross the boundary as raw device pointers (``Tensor.data_ptr()``) plus
+sizes and the current CUDA stream; PyTorch is only the allocator / stream provider.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libf2nerf_b200.so")
+
+
+class F2BError(RuntimeError):
+    """Raised when a C-ABI call returns a negative status (message from f2b_last_error)."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"f2nerf_b200: CUDA extension {LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make`) first; there is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.f2b_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+lib = _load()
+
+c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64
+
+# name -> argtypes (restype is always int).  Keep in the order of include/f2nerf_b200.h.
+_P = c_void_p
+SIGNATURES = {
+    "f2b_abi_version": [],
+    "f2b_device_info": [_P, _P],
+    "f2b_sampler_count": [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_int, c_int, _P, _P, _P, _P],
+    "f2b_sampler_fill": [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_edge_samples": [_P, _P, _P, _P, c_int, _P, _P, _P],
+    "f2b_oct_mark_visit": [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_oct_update_stats": [_P, _P, _P, _P, _P, _P, c_int, _P],
+    "f2b_hash_level_scales": [_P],
+    "f2b_table_to_half": [_P, _P, c_i64, _P],
+    "f2b_hash_fwd": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P],
+    "f2b_hash_bwd": [_P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
+    "f2b_mlp_fwd": [_P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_mlp_bwd": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_mlp_fwd_v0": [_P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_mlp_bwd_v0": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_set_mlp_impl": [c_int],
+    "f2b_get_mlp_impl": [],
+    "f2b_cast_f32_to_f16": [_P, _P, c_i64, c_float, _P],
+    "f2b_cast_f16_to_f32": [_P, _P, c_i64, c_float, _P],
+    "f2b_sh_encode": [_P, c_int, c_int, _P, _P],
+    "f2b_scatter_idx": [_P, _P, c_int, _P, _P],
+    "f2b_shader_prep": [_P, _P, _P, _P, c_int, _P, _P],
+    "f2b_shader_act": [_P, c_int, _P, _P],
+    "f2b_shader_act_bwd": [_P, _P, c_int, c_float, _P, _P],
+    "f2b_shader_prep_bwd": [_P, _P, c_int, c_float, c_int, _P, _P, _P],
+    "f2b_early_stop": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_compact_samples": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_composite_fwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "f2b_composite_bwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, _P],
+    "f2b_flex_sum": [_P, c_int, _P, c_int, _P, _P],
+    "f2b_flex_accumulate_sum": [_P, _P, c_int, c_int, _P, _P],
+    "f2b_weight_var_fwd": [_P, _P, c_int, _P, _P],
+    "f2b_weight_var_bwd": [_P, _P, c_int, _P, _P, _P],
+}
+
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly
+    _fn.argtypes = _args
+    _fn.restype = c_int
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous tensor, None -> NULL."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        if not t.is_contiguous():
+            raise ValueError("f2nerf_b200: tensor crossing the C ABI must be contiguous")
+        return t.data_ptr()
+    return t
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# kernels launched per entry point (for bench.py's gpu_launches claim; memsets are not counted)
+KERNELS_PER_CALL = {"f2b_sampler_count": 2, "f2b_early_stop": 2, "f2b_hash_level_scales": 1, "f2b_device_info": 0,
+                    "f2b_abi_version": 0, "f2b_set_mlp_impl": 0, "f2b_get_mlp_impl": 0}
+LAUNCHES = 0      # running count of product kernels launched through this binding
+TRACE = None      # set to a list to record (name, start_event, end_event, int_args) per call (bench.py)
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; tensors are passed by pointer; raises F2BError on failure."""
+    global LAUNCHES
+    fn = getattr(lib, name)
+    conv = [ptr(a) if isinstance(a, torch.Tensor) or a is None else a for a in args]
+    if TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*conv)
+        e1.record()
+        TRACE.append((name, e0, e1, [a for a in args if isinstance(a, int) and not isinstance(a, bool)]))
+    else:
+        rc = fn(*conv)
+    if rc != 0:
+        raise F2BError(f"{name} -> {rc}: {lib.f2b_last_error().decode()}")
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    return rc

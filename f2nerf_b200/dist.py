@@ -1,0 +1,69 @@
+"""Data-parallel plumbing: rays are sharded across ranks (one process per GPU), the hash table, MLPs,
+appearance embedding and octree are replicated; after backward exactly one exchange step runs
+(SURVEY.md §8e).  No collective sits inside the data path (forward / backward kernels).
+
+  * SUM all-reduce of the hash-table gradient — only the live prefix: level l occupies halves
+    [l*S, l*S + 2S) so rows >= 17*S/2 of the [pool,2] gradient are identically zero (the reference's
+    overlapping-level quirk) and are never sent;
+  * one flattened SUM all-reduce for the two MLP gradients + the appearance-embedding gradient;
+  * MAX all-reduce (int32) of the octree votes BEFORE the stat update, so every rank prunes the same
+    nodes (PersSampler.cu:579-603 would otherwise diverge across ranks);
+  * OR of the NaN flag, MEAN of the samples-per-ray EMAs that size the next batch (ExpRunner.cpp:86).
+Gradients are averaged (losses are means over the global batch).
+"""
+import torch
+import torch.distributed as dist
+
+
+def live_rows(field):
+    return min(field.feat_pool_.shape[0], (17 * field.local_size_) // 2)
+
+
+def install_vote_sync(sampler):
+    """Make UpdateOctNodes all-reduce its votes (MAX) across ranks before applying them."""
+    def sync(vote_w, vote_a, mark, visit_cnt):
+        n = vote_w.numel()
+        flat = torch.cat([vote_w, vote_a, mark, visit_cnt])
+        dist.all_reduce(flat, op=dist.ReduceOp.MAX)
+        vote_w.copy_(flat[:n]); vote_a.copy_(flat[n:2 * n]); mark.copy_(flat[2 * n:3 * n]); visit_cnt.copy_(flat[3 * n:])
+    sampler.vote_allreduce_ = sync
+
+
+def allreduce_grads(renderer):
+    """The post-backward exchange step; returns the number of bytes each rank contributed."""
+    world = dist.get_world_size()
+    field, shader = renderer.scene_field_, renderer.shader_
+    small = [p for p in (field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_) if p.grad is not None]
+    sent = 0
+    if field.feat_pool_.grad is not None:
+        g = field.feat_pool_.grad[:live_rows(field)]
+        dist.all_reduce(g)
+        g.div_(world)
+        sent += g.numel() * g.element_size()
+    if small:
+        flat = torch.cat([p.grad.reshape(-1) for p in small])
+        flag = getattr(renderer, "nonfinite_flag_", None)
+        flat = torch.cat([flat, (flag if flag is not None else torch.zeros((), dtype=torch.bool, device=flat.device)).float().reshape(1) * world])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for p in small:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad)); off += n
+        renderer.nonfinite_flag_ = flat[off] > 0            # OR across ranks
+        sent += flat.numel() * 4
+    return sent
+
+
+def sync_emas(gdp):
+    t = torch.tensor([gdp.sampled_oct_per_ray_, gdp.sampled_pts_per_ray_, gdp.meaningful_sampled_pts_per_ray_], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t)
+    t = (t / dist.get_world_size()).tolist()
+    gdp.sampled_oct_per_ray_, gdp.sampled_pts_per_ray_, gdp.meaningful_sampled_pts_per_ray_ = t
+
+
+def allreduce_step(prob):
+    """bench.py hook: the exchange step of one training iteration."""
+    allreduce_grads(prob["renderer"])

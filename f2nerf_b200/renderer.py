@@ -1,0 +1,198 @@
+"""Renderer — host-side mirror of ``src/Renderer/Renderer.{h,cpp,cu}``: orchestrates one ray batch
+through sampler -> field (no-grad early-stop pass) -> compaction -> field -> shader -> composite.
+
+``Renderer.Render`` returns the reference's ``RenderResult`` (Renderer.h:18-27) and is connected by
+ONE autograd node to the four leaves the trainer optimises (``feat_pool_``, the two ``mlp_.params_``,
+``app_emb_`` — ExpRunner.cpp:54,129-136); its backward is a fixed sequence of C-ABI kernels
+(composite bwd -> shader MLP bwd -> field MLP bwd -> hash scatter) instead of ~60 autograd nodes.
+Host syncs per call: 2 (sample total, survivor total) against the reference's >= 11 ``.item()`` calls.
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .field import field_backward, field_forward
+from .sampler import TRAIN, VALIDATE, SampleResultFlex
+
+N_EDGE_PTS = 8192
+
+
+@dataclass
+class RenderResult:
+    """``struct RenderResult`` (src/Renderer/Renderer.h:18-27)."""
+    colors: torch.Tensor
+    first_oct_dis: torch.Tensor
+    disparity: torch.Tensor
+    edge_feats: Optional[torch.Tensor]
+    depth: torch.Tensor
+    weights: Optional[torch.Tensor]
+    idx_start_end: Optional[torch.Tensor]
+
+
+class Renderer:
+    def __init__(self, global_data_pool, pts_sampler, scene_field, shader, n_images, use_app_emb=False,
+                 bg_color="rand_noise", device="cuda"):
+        self.global_data_pool_ = global_data_pool
+        self.pts_sampler_, self.scene_field_, self.shader_ = pts_sampler, scene_field, shader
+        self.use_app_emb_ = bool(use_app_emb)
+        self.app_emb_ = (torch.randn((n_images, 16), dtype=torch.float32, device=device) * .1).requires_grad_(True)
+        if bg_color not in ("white", "black", "rand_noise"):
+            bg_color = "rand_noise"
+        self.bg_color_type_ = bg_color
+        self.sample_result_ = None
+
+    # ------------------------------------------------------------------------------------------
+    def _bg(self, n_rays, dev):
+        gdp = self.global_data_pool_
+        if self.bg_color_type_ == "white":
+            return torch.ones((n_rays, 3), dtype=torch.float32, device=dev)
+        if self.bg_color_type_ == "rand_noise":
+            if gdp.mode_ == TRAIN:
+                return torch.rand((n_rays, 3), dtype=torch.float32, device=dev)
+            return torch.ones((n_rays, 3), dtype=torch.float32, device=dev) * .5
+        return torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
+
+    def Render(self, rays_o, rays_d, bounds, emb_idx=None):
+        """Renderer::Render (Renderer.cpp:52-213)."""
+        gdp = self.global_data_pool_
+        field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
+        n_rays, dev = rays_o.shape[0], rays_o.device
+        train = gdp.mode_ == TRAIN
+        sr = sampler.GetSamples(rays_o, rays_d, bounds)
+        self.sample_result_ = sr
+        n_all = sr.pts.shape[0]
+        if train and n_rays > 0:
+            gdp.sampled_pts_per_ray_ = gdp.sampled_pts_per_ray_ * .9 + (n_all / n_rays) * .1
+        bg = self._bg(n_rays, dev)
+        if n_all <= 0:
+            if train:
+                gdp.meaningful_sampled_pts_per_ray_ *= .9
+            z = torch.zeros
+            return RenderResult(bg, z((n_rays, 1), device=dev), z((n_rays,), device=dev), None,
+                                torch.full((n_rays,), 512., device=dev), None, None)
+
+        # ---- early stop: inference only (Renderer.cpp:107-150) --------------------------------
+        with torch.no_grad():
+            table16 = field.table_f16()
+            fparams16 = field.mlp_.params_f16()
+            feat_all, _, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False)
+            weights0, alphas0, keep, new_bounds, total = ops.early_stop(feat_all, 16, sr.dt, sr.pts_idx_bounds)
+            n_kept = int(total.item())                                               # sync 2
+            if train:
+                sampler.UpdateOctNodes(sr, weights0, alphas0)
+                gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
+            pts, dirs, dt, t, anchors = ops.compact_samples(keep, sr.pts_idx_bounds, new_bounds, n_kept, sr.pts,
+                                                            sr.dirs, sr.dt, sr.t, sr.anchors)
+            es = SampleResultFlex(pts, dirs, dt, t, anchors, new_bounds, sr.first_oct_dis.clone())
+            if train:                                                                 # TV-loss edge points
+                edge_pts, edge_anchors = sampler.GetEdgeSamples(N_EDGE_PTS)
+                q_pts = torch.cat([pts, edge_pts.reshape(N_EDGE_PTS * 2, 3)], 0)
+                q_anchors = torch.cat([anchors[:, 0], edge_anchors.reshape(N_EDGE_PTS * 2)], 0).contiguous()
+            else:
+                q_pts, q_anchors = pts, anchors[:, 0].contiguous()
+            pt_emb_idx = None
+            if train and self.use_app_emb_:
+                pt_emb_idx = ops.scatter_idx(n_kept, new_bounds, emb_idx.to(torch.int32).contiguous())
+
+        grad_on = torch.is_grad_enabled() and train
+        args = (self, es, q_pts, q_anchors, pt_emb_idx, bg, table16, n_kept, grad_on)
+        colors, disparity, depth, weights, edge_feats = _RenderFunction.apply(
+            field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, *args)
+        if not train:
+            edge_feats = None
+        return RenderResult(colors, es.first_oct_dis, disparity, edge_feats, depth, weights, new_bounds)
+
+    # ------------------------------------------------------------------------------------------
+    def States(self):
+        out = []
+        for p in (self.pts_sampler_, self.scene_field_, self.shader_):
+            out += p.States()
+        return out + [self.app_emb_.data]
+
+    def LoadStates(self, states, idx=0):
+        for p in (self.pts_sampler_, self.scene_field_, self.shader_):
+            idx = p.LoadStates(states, idx)
+        self.app_emb_.data.copy_(states[idx].to(self.app_emb_.device)); idx += 1
+        return idx
+
+    def OptimParamGroups(self):
+        lr = self.global_data_pool_.learning_rate_
+        groups = self.scene_field_.OptimParamGroups() + self.shader_.OptimParamGroups()
+        return groups + [dict(params=[self.app_emb_], lr=lr, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6)]
+
+    def Reset(self):
+        self.scene_field_.Reset()
+        self.shader_.Reset()
+
+
+class _RenderFunction(torch.autograd.Function):
+    """Second half of Renderer::Render (Renderer.cpp:152-208) with its whole backward."""
+
+    @staticmethod
+    def forward(ctx, feat_pool, field_params, shader_params, app_emb, renderer, es, q_pts, q_anchors, pt_emb_idx, bg,
+                table16, n_kept, grad_on):
+        field, shader = renderer.scene_field_, renderer.shader_
+        fparams16 = ops.cast_f32_to_f16(field_params)
+        sparams16 = ops.cast_f32_to_f16(shader_params)
+        scene_feat, feat16, f_hidden = field_forward(field, table16, fparams16, q_pts, q_anchors, 1, save=grad_on)
+        emb = app_emb if pt_emb_idx is not None else None
+        mlp_in = ops.shader_prep(scene_feat, es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
+            torch.empty((0, 32), dtype=torch.float16, device=bg.device)
+        raw, s_hidden = ops.mlp_fwd(mlp_in, sparams16, shader.mlp_.n_hidden_matmuls, save_hidden=grad_on)
+        rgb = ops.shader_act(raw)
+        colors, disparity, depth, weights = ops.composite_fwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg)
+        edge_feats = scene_feat[n_kept:].reshape(-1, 2, 16)
+        ctx.renderer, ctx.es, ctx.n_kept = renderer, es, n_kept
+        ctx.pack = (fparams16, sparams16, q_pts, q_anchors, pt_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
+                    s_hidden, rgb)
+        ctx.gs_progress = renderer.global_data_pool_.gradient_scaling_progress_
+        return colors, disparity, depth, weights, edge_feats
+
+    @staticmethod
+    def backward(ctx, d_colors, d_disp, d_depth, d_weights, d_edge):
+        renderer, es, n_kept = ctx.renderer, ctx.es, ctx.n_kept
+        field, shader, gdp = renderer.scene_field_, renderer.shader_, renderer.global_data_pool_
+        (fparams16, sparams16, q_pts, q_anchors, pt_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
+         rgb) = ctx.pack
+        if feat16 is None:
+            raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
+        n_q, dev = q_pts.shape[0], q_pts.device
+        n_rays = es.pts_idx_bounds.shape[0]
+        zeros = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        d_colors = d_colors.contiguous() if d_colors is not None else zeros(n_rays, 3)
+        d_disp = d_disp.contiguous() if d_disp is not None else None
+        d_depth = d_depth.contiguous() if d_depth is not None else None
+        d_weights = d_weights.contiguous() if d_weights is not None else None
+        d_scene = zeros(n_q, 16)
+        if d_edge is not None:
+            d_scene[n_kept:] = d_edge.reshape(-1, 16)
+        # composite (+TruncExp, +GradientScaling) -> d logit (column 0 of d_scene), d rgb
+        d_rgb = ops.composite_bwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg, d_colors, d_disp, d_depth,
+                                  d_weights, ctx.gs_progress, d_scene, 16)
+        # shader: sigmoid -> MLP -> input assembly
+        s_scale = shader.mlp_.loss_scale_
+        d_raw = ops.shader_act_bwd(raw, d_rgb, s_scale)
+        d_in16, d_sparams = ops.mlp_bwd(d_raw, mlp_in, s_hidden, sparams16, shader.mlp_.n_hidden_matmuls, need_din=True)
+        d_sparams = d_sparams / s_scale
+        d_app = torch.zeros_like(renderer.app_emb_) if pt_emb_idx is not None else None
+        ops.shader_prep_bwd(d_in16, pt_emb_idx, 1.0 / s_scale, renderer.app_emb_.shape[0], d_scene, d_app)
+        # field: MLP -> hash scatter
+        d_table, d_fparams = field_backward(field, fparams16, q_pts, q_anchors, 1, feat16, f_hidden, d_scene)
+        # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
+        bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
+        renderer.nonfinite_flag_ = bad
+        return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None
+
+
+def check_backward_nan(renderer):
+    """Host read of the device-side NaN flag set by the last backward (one sync); applies the reference's
+    loss-scale halving and sets ``global_data_pool_.backward_nan_`` (ExpRunner.cpp:131-134 reads it)."""
+    flag = getattr(renderer, "nonfinite_flag_", None)
+    if flag is not None and bool(flag.item()):
+        renderer.global_data_pool_.backward_nan_ = True
+        for m in (renderer.scene_field_.mlp_, renderer.shader_.mlp_):
+            m.loss_scale_ = max(m.loss_scale_ / 2.0, 1.0)
+        return True
+    return False

@@ -118,22 +118,38 @@ int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_sav
 int f2b_cast_f32_to_f16(const float* src, void* dst, int64_t n, float scale, void* stream);
 int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
 
-/* Fused field forward: hash encode + MLP(32->64->16), encoded features never touch HBM unless
- * feat_save is given (backward needs them).  out: [P,16] fp32 (fp16-rounded values, as TCNNWP::Query). */
-int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool,
-                  int n_volumes, int local_size, const void* mlp_params_f16,
-                  const float* pts, const int* vol, int vol_stride, int n_pts,
-                  float* out_f32, void* feat_save_f16, void* hidden_save_f16, void* stream);
+/* Implementation selection for f2b_mlp_fwd / f2b_mlp_bwd: 1 = tcgen05/TMEM kernels (default when
+ * built), 0 = CUDA-core twin (validation).  Env F2B_MLP_IMPL overrides the default. */
+int f2b_set_mlp_impl(int impl);
+int f2b_get_mlp_impl(void);
+int f2b_mlp_fwd_v0(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                   void* out_f16, void* hidden_save_f16, void* stream);
+int f2b_mlp_bwd_v0(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                   const void* params_f16, int n_hidden_matmuls, int n_pts,
+                   void* din_f16, float* dparams_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Shader — replaces SHShader::Query (src/Shader/SHShader.cpp:23-29, SHShader.cu:10-118).
  * ------------------------------------------------------------------------------------------ */
-int f2b_sh_encode(const float* dirs, int n_pts, int degree, float* out, void* stream);
-/* Fused: in = [shading_feat(16) | SH4(dir)(16)] -> fp16 -> MLP(32->64->64->16) -> rgb = 1.002*sigmoid(o)-0.001.
- * mlp_in_save [P,32] fp16, hidden_save [2,P,64] fp16, raw_out_save [P,16] fp16: nullable (for backward). */
-int f2b_shader_fwd(const float* shading_feat /* [P,16] */, const float* dirs /* [P,3] */,
-                   const void* mlp_params_f16, int n_pts, float* rgb /* [P,3] */,
-                   void* mlp_in_save_f16, void* hidden_save_f16, void* raw_out_save_f16, void* stream);
+int f2b_sh_encode(const float* dirs, int n_pts, int degree /* 1..4 */, float* out, void* stream);
+/* CustomOps::ScatterIdx (Scatter.cu:110-131): per-ray camera index broadcast to the ray's samples. */
+int f2b_scatter_idx(const int* pts_idx_bounds, const int* emb_idx, int n_rays, int* out, void* stream);
+/* Shader-MLP input assembly (Renderer.cpp:179-187 + SHShader.cpp:24-25 + tcnn identity cast):
+ * mlp_in[p] = fp16([1, scene_feat[p,1:16]] + app_emb[pt_emb_idx[p]] | SH4(dirs[p])); app_emb nullable. */
+int f2b_shader_prep(const float* scene_feat /* [P,16] */, const float* dirs /* [P,3] */,
+                    const float* app_emb /* [n_img,16] or NULL */, const int* pt_emb_idx /* [P] or NULL */,
+                    int n_pts, void* mlp_in_f16 /* [P,32] */, void* stream);
+/* rgb = (1+2e-3)*sigmoid(raw[:, :3]) - 1e-3 on the fp16 MLP output (SHShader.cpp:27-28). */
+int f2b_shader_act(const void* raw_out_f16 /* [P,16] */, int n_pts, float* rgb /* [P,3] */, void* stream);
+/* Backward of the activation: d_raw[P,16] fp16 = loss_scale * d_rgb * sigmoid' (channels 3..15 zero). */
+int f2b_shader_act_bwd(const void* raw_out_f16, const float* d_rgb, int n_pts, float loss_scale,
+                       void* d_raw_f16, void* stream);
+/* Backward of the input assembly: d_scene_feat[p,1:16] = d_mlp_in[p,1:16]*inv_loss_scale (column 0 is left
+ * to the composite backward) and, when d_app_emb != NULL, d_app_emb[cam] += d_mlp_in[p,0:16]
+ * (ScatterAddFuncBackwardBlock, Scatter.cu:23-40). */
+int f2b_shader_prep_bwd(const void* d_mlp_in_f16 /* [P,32] */, const int* pt_emb_idx, int n_pts,
+                        float inv_loss_scale, int n_emb, float* d_scene_feat /* [P,16] */,
+                        float* d_app_emb /* [n_emb,16] or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Composite — replaces the Renderer::Render tail (src/Renderer/Renderer.cpp:107-150,196-208),

@@ -1,0 +1,211 @@
+// ref_driver.cpp — harness around the UNMODIFIED reference operators (Totoro97/f2-nerf @98f0daa),
+// linked from the reference's own sources by oracle/Makefile.ref into oracle/_ref/ref_driver.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/f2_oracle.c header).  It constructs the reference's
+// GlobalDataPool / Dataset / Renderer exactly like ExpRunner::ExpRunner does (src/ExpRunner.cpp:17-63),
+// then (1) dumps the octree / warp / hash blobs, (2) runs PersSampler::GetSamples,
+// Hash3DAnchored::AnchoredQuery, SHShader::Query and Renderer::Render (+ backward) on fixed seeded
+// inputs and dumps every boundary tensor as .npy, (3) times Render + backward with CUDA events.
+// The dumps pin oracle/f2_oracle.c and the CUDA kernels (tests/golden/, tests/test_ref_parity.py).
+//
+//   ref_driver <runtime_config.yaml> <out_dir> <n_rays> [n_time_iters=0] [dump_full_grads=0]
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <experimental/filesystem>
+#include <torch/torch.h>
+#include <cuda_runtime.h>
+#include "Common.h"
+#include "Utils/GlobalDataPool.h"
+#include "Utils/cnpy.h"
+#include "Utils/CustomOps/CustomOps.h"
+#include "Dataset/Dataset.h"
+#include "Renderer/Renderer.h"
+#include "PtsSampler/PersSampler.h"
+#include "Field/Hash3DAnchored.h"
+#include "Shader/SHShader.h"
+
+namespace fs = std::experimental::filesystem::v1;
+using Tensor = torch::Tensor;
+
+static std::string g_out;
+
+static void dump(const std::string& name, const Tensor& t_in) {
+  Tensor t = t_in.detach().to(torch::kCPU).contiguous();
+  std::vector<size_t> shape;
+  for (auto s : t.sizes()) shape.push_back((size_t)s);
+  if (shape.empty()) shape.push_back(1);
+  const std::string path = g_out + "/" + name + ".npy";
+  switch (t.scalar_type()) {
+    case torch::kFloat32: cnpy::npy_save(path, t.data_ptr<float>(), shape); break;
+    case torch::kInt32: cnpy::npy_save(path, t.data_ptr<int>(), shape); break;
+    case torch::kInt64: cnpy::npy_save(path, t.data_ptr<int64_t>(), shape); break;
+    case torch::kUInt8: cnpy::npy_save(path, t.data_ptr<uint8_t>(), shape); break;
+    case torch::kBool: { Tensor u = t.to(torch::kUInt8); cnpy::npy_save(path, u.data_ptr<uint8_t>(), shape); break; }
+    default: std::cerr << "dump: unsupported dtype for " << name << std::endl; std::exit(2);
+  }
+}
+static void dump_scalar(const std::string& name, float v) { dump(name, torch::full({1}, v, CPUFloat)); }
+
+int main(int argc, char** argv) {
+  if (argc < 4) { std::fprintf(stderr, "usage: ref_driver <config.yaml> <out_dir> <n_rays> [n_time_iters] [dump_full_grads]\n"); return 1; }
+  const std::string conf_path = argv[1];
+  g_out = argv[2];
+  const int n_rays = std::atoi(argv[3]);
+  const int n_time = argc > 4 ? std::atoi(argv[4]) : 0;
+  const int full_grads = argc > 5 ? std::atoi(argv[5]) : 0;
+  fs::create_directories(g_out);
+
+  torch::manual_seed(2022);   // main.cpp:8
+  auto gdp = std::make_unique<GlobalDataPool>(conf_path);
+  gdp->base_exp_dir_ = gdp->config_["base_exp_dir"].as<std::string>();
+  fs::create_directories(gdp->base_exp_dir_);
+  gdp->learning_rate_ = 1e-2f;
+  auto dataset = std::make_unique<Dataset>(gdp.get());
+  auto renderer = std::make_unique<Renderer>(gdp.get(), dataset->n_images_);
+  auto* sampler = dynamic_cast<PersSampler*>(renderer->pts_sampler_.get());
+  auto* field = dynamic_cast<Hash3DAnchored*>(renderer->scene_field_.get());
+  auto* shader = dynamic_cast<SHShader*>(renderer->shader_.get());
+  CHECK(sampler && field && shader);
+
+  // ---- deterministic, non-trivial parameters (reproducible from the CPU generator in Python) ----
+  {
+    auto g = at::detail::createCPUGenerator(1234);
+    Tensor feat = (torch::rand({field->pool_size_, 2}, g, CPUFloat) * 2.f - 1.f);      // U(-1,1)
+    field->feat_pool_.data().copy_(feat.to(torch::kCUDA));
+    field->mlp_->params_.data().mul_(4.f);          // wider density range so early stop triggers
+    renderer->app_emb_.data().copy_((torch::rand({dataset->n_images_, 16}, g, CPUFloat) * .2f - .1f).to(torch::kCUDA));
+  }
+
+  // ---- scene blobs & scalars --------------------------------------------------------------------
+  dump("tree_nodes", sampler->pers_octree_->tree_nodes_gpu_);
+  dump("pers_trans", sampler->pers_octree_->pers_trans_gpu_);
+  dump("edge_pool", sampler->pers_octree_->edge_pool_gpu_);
+  dump("search_order", sampler->pers_octree_->node_search_order_);
+  dump("prim_pool", field->prim_pool_);
+  dump("bias_pool", field->bias_pool_);
+  dump("field_mlp_params", field->mlp_->params_);
+  dump("shader_mlp_params", shader->mlp_->params_);
+  dump("app_emb", renderer->app_emb_);
+  {
+    Tensor sc = torch::zeros({8}, CPUFloat);
+    sc[0] = sampler->global_near_; sc[1] = sampler->sample_l_; sc[2] = sampler->scale_by_dis_ ? 1.f : 0.f;
+    sc[3] = float(sampler->max_oct_intersect_per_ray_); sc[4] = float(field->n_volumes_);
+    sc[5] = float(field->pool_size_); sc[6] = float(dataset->n_images_); sc[7] = float(n_rays);
+    dump("scalars", sc);
+  }
+
+  // ---- rays ---------------------------------------------------------------------------------------
+  torch::manual_seed(2023);
+  auto [rays, gt_colors, emb_idx] = dataset->RandRaysData(n_rays, DATA_TRAIN_SET);
+  Tensor rays_o = rays.origins.contiguous(), rays_d = rays.dirs.contiguous(), bounds = rays.bounds.contiguous();
+  dump("rays_o", rays_o); dump("rays_d", rays_d); dump("gt_colors", gt_colors); dump("emb_idx", emb_idx);
+  dump("rays_d_normed", (rays_d / torch::linalg_norm(rays_d, 2, -1, true)).contiguous());
+
+  // ---- sampler, VALIDATE mode (noise == 1) --------------------------------------------------------
+  gdp->iter_step_ = 1;
+  gdp->ray_march_fineness_ = 1.f;
+  gdp->gradient_scaling_progress_ = 0.25f;   // exercise GradientScaling
+  gdp->mode_ = RunningMode::VALIDATE;
+  {
+    torch::NoGradGuard ng;
+    auto s = sampler->GetSamples(rays_o, rays_d, bounds);
+    dump("val_pts", s.pts); dump("val_dirs", s.dirs); dump("val_dt", s.dt); dump("val_t", s.t);
+    dump("val_anchors", s.anchors.index({Slc(), Slc(0, 2)}).contiguous());
+    dump("val_bounds", s.pts_idx_bounds); dump("val_first_oct_dis", s.first_oct_dis);
+    Tensor feat = field->AnchoredQuery(s.pts, s.anchors.index({"...", 0}).contiguous());
+    dump("val_scene_feat", feat);
+    Tensor shading = torch::cat({torch::ones_like(feat.index({Slc(), Slc(0, 1)})), feat.index({Slc(), Slc(1, None)})}, 1);
+    dump("val_rgb", shader->Query(shading, s.dirs));
+    auto r = renderer->Render(rays_o, rays_d, bounds, Tensor());
+    dump("val_colors", r.colors); dump("val_disparity", r.disparity); dump("val_depth", r.depth);
+    dump("val_weights", r.weights); dump("val_idx_start_end", r.idx_start_end);
+  }
+
+  // ---- TRAIN mode: seeded RNG, replayed once to expose the internal draws -------------------------
+  gdp->mode_ = RunningMode::TRAIN;
+  const int64_t seed = 777;
+  {
+    torch::manual_seed(seed);
+    Tensor noise = ((torch::rand({1024 + n_rays + 10}, CUDAFloat) - .5f) + 1.f).contiguous();   // PersSampler.cu:377
+    noise.mul_(gdp->ray_march_fineness_);
+    Tensor bg = torch::rand({n_rays, 3}, CUDAFloat);                                               // Renderer.cpp:73
+    int n_edges = sampler->pers_octree_->edge_pool_.size();
+    Tensor edge_idx = torch::randint(0, n_edges, {8192}, CUDAInt);                                 // PersSampler.cu:456
+    Tensor edge_coord = torch::rand({8192, 2}, CUDAFloat) * 2.f - 1.f;                             // :457
+    dump("train_noise", noise); dump("train_bg", bg); dump("train_edge_idx", edge_idx); dump("train_edge_coord", edge_coord);
+  }
+  Tensor stats_w0 = sampler->pers_octree_->tree_weight_stats_.clone();
+  {
+    torch::manual_seed(seed);
+    auto r = renderer->Render(rays_o, rays_d, bounds, emb_idx);
+    dump("train_colors", r.colors); dump("train_disparity", r.disparity); dump("train_depth", r.depth);
+    dump("train_weights", r.weights); dump("train_idx_start_end", r.idx_start_end);
+    dump("train_first_oct_dis", r.first_oct_dis); dump("train_edge_feats", r.edge_feats);
+    const auto& s = renderer->sample_result_;
+    dump("train_pts", s.pts); dump("train_dt", s.dt); dump("train_t", s.t);
+    dump("train_anchors", s.anchors.index({Slc(), Slc(0, 2)}).contiguous()); dump("train_bounds", s.pts_idx_bounds);
+    dump("train_tree_nodes_after", sampler->pers_octree_->tree_nodes_gpu_);
+    dump("train_weight_stats_after", sampler->pers_octree_->tree_weight_stats_);
+    dump("train_alpha_stats_after", sampler->pers_octree_->tree_alpha_stats_);
+    dump("train_visit_cnt_after", sampler->pers_octree_->tree_visit_cnt_);
+
+    // losses as ExpRunner::Train (src/ExpRunner.cpp:94-118), fixed weights
+    Tensor color_loss = torch::sqrt((r.colors - gt_colors).square() + 1e-4f).mean();
+    Tensor disparity_loss = r.disparity.square().mean();
+    Tensor tv_loss = (r.edge_feats.index({Slc(), 0}) - r.edge_feats.index({Slc(), 1})).square().mean();
+    Tensor var_loss = (CustomOps::WeightVar(r.weights, r.idx_start_end) + 1e-2).sqrt().mean();
+    Tensor loss = color_loss + var_loss * 1e-2f + disparity_loss * 1e-2f + tv_loss * 1e-1f;
+    dump("train_loss", loss.reshape({1}));
+    loss.backward();
+    dump("grad_field_mlp", field->mlp_->params_.grad());
+    dump("grad_shader_mlp", shader->mlp_->params_.grad());
+    dump("grad_app_emb", renderer->app_emb_.grad());
+    Tensor g = field->feat_pool_.grad().reshape({-1});
+    if (full_grads) dump("grad_feat_pool", g);
+    Tensor nz = torch::nonzero(g).reshape({-1});
+    dump("grad_feat_pool_nz_idx", nz.to(torch::kInt32));
+    dump("grad_feat_pool_nz_val", g.index({nz}));
+    dump_scalar("backward_nan", gdp->backward_nan_ ? 1.f : 0.f);
+  }
+
+  // ---- timing: Render + backward, CUDA events on the default stream ------------------------------
+  if (n_time > 0) {
+    std::vector<float> ms_fwd, ms_all;
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    double samples = 0, kept = 0;
+    for (int it = 0; it < n_time + 5; it++) {
+      gdp->iter_step_ = 1 + it * 2 + 1;      // never a multiple of compact_freq / milestone
+      field->feat_pool_.mutable_grad() = Tensor(); field->mlp_->params_.mutable_grad() = Tensor();
+      shader->mlp_->params_.mutable_grad() = Tensor(); renderer->app_emb_.mutable_grad() = Tensor();
+      torch::cuda::synchronize();
+      cudaEventRecord(e0, 0);
+      auto r = renderer->Render(rays_o, rays_d, bounds, emb_idx);
+      cudaEventRecord(e1, 0);
+      Tensor color_loss = torch::sqrt((r.colors - gt_colors).square() + 1e-4f).mean();
+      Tensor tv_loss = (r.edge_feats.index({Slc(), 0}) - r.edge_feats.index({Slc(), 1})).square().mean();
+      Tensor var_loss = (CustomOps::WeightVar(r.weights, r.idx_start_end) + 1e-2).sqrt().mean();
+      Tensor loss = color_loss + var_loss * 1e-2f + tv_loss * 1e-1f;
+      loss.backward();
+      cudaEventRecord(e2, 0);
+      torch::cuda::synchronize();
+      float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e0, e2);
+      if (it >= 5) { ms_fwd.push_back(a); ms_all.push_back(b); samples += renderer->sample_result_.pts.size(0); kept += r.weights.size(0); }
+    }
+    std::sort(ms_fwd.begin(), ms_fwd.end()); std::sort(ms_all.begin(), ms_all.end());
+    const float mf = ms_fwd[ms_fwd.size() / 2], ma = ms_all[ms_all.size() / 2];
+    std::printf("{\"ref_timing\": {\"n_rays\": %d, \"iters\": %d, \"ms_fwd_median\": %.4f, \"ms_fwd_bwd_median\": %.4f, "
+                "\"samples_per_ray\": %.2f, \"kept_per_ray\": %.2f, \"rays_per_s\": %.1f}}\n",
+                n_rays, n_time, mf, ma, samples / n_time / n_rays, kept / n_time / n_rays, n_rays / (ma * 1e-3));
+    FILE* f = std::fopen((g_out + "/ref_timing.json").c_str(), "w");
+    std::fprintf(f, "{\"n_rays\": %d, \"iters\": %d, \"ms_fwd_median\": %.4f, \"ms_fwd_bwd_median\": %.4f, "
+                 "\"samples_per_ray\": %.2f, \"kept_per_ray\": %.2f, \"rays_per_s\": %.1f}\n",
+                 n_rays, n_time, mf, ma, samples / n_time / n_rays, kept / n_time / n_rays, n_rays / (ma * 1e-3));
+    std::fclose(f);
+  }
+  std::printf("ref_driver: done, dumps in %s\n", g_out.c_str());
+  return 0;
+}

