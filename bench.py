@@ -254,7 +254,7 @@ def reference_gpu_timing(args):
     if args.no_ref_gpu or not os.path.exists(drv) or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return None
     try:
-        out_dir = os.path.join(ROOT, "gpurun_out", "ref_bench")
+        out_dir = "/tmp/f2b_ref_bench"
         subprocess.run([drv, os.path.join(ROOT, "oracle", "ref_config_ngp_fox.yaml"), out_dir, str(args.rays), "20"],
                        cwd=ROOT, capture_output=True, text=True, timeout=600)
         return json.load(open(os.path.join(out_dir, "ref_timing.json")))

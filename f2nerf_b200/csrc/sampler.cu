@@ -413,10 +413,12 @@ extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void
                                  int max_oct_intersect_per_ray, int* ray_counts, int* pts_idx_bounds,
                                  int* totals, void* stream) {
   F2B_REQUIRE(n_rays >= 0 && n_nodes > 0 && n_trans >= 0, "f2b_sampler_count: bad sizes");
-  F2B_REQUIRE(tree_nodes && trans && ray_counts && pts_idx_bounds && totals, "f2b_sampler_count: null pointer");
+  F2B_REQUIRE(totals, "f2b_sampler_count: null totals");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(totals, 0, 2 * sizeof(int), st);
-  if (n_rays == 0) return check_launch("f2b_sampler_count");
+  if (n_rays == 0) return check_launch("f2b_sampler_count");      // empty batch: totals = {0, 0}
+  F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && ray_counts && pts_idx_bounds,
+              "f2b_sampler_count: null pointer");
   march_kernel<false><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
       far, sample_l, scale_by_dis, max_oct_intersect_per_ray, ray_counts, totals + 1, nullptr, nullptr,

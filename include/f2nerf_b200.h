@@ -127,6 +127,11 @@ int f2b_mlp_fwd_v0(const void* in_f16, const void* params_f16, int n_hidden_matm
 int f2b_mlp_bwd_v0(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
                    const void* params_f16, int n_hidden_matmuls, int n_pts,
                    void* din_f16, float* dparams_f32, void* stream);
+int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                   void* out_f16, void* hidden_save_f16, void* stream);
+int f2b_mlp_bwd_tc(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                   const void* params_f16, int n_hidden_matmuls, int n_pts,
+                   void* din_f16, float* dparams_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Shader — replaces SHShader::Query (src/Shader/SHShader.cpp:23-29, SHShader.cu:10-118).

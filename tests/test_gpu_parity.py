@@ -154,7 +154,7 @@ def test_hash_bwd_matches_exact_sum(scene, oracle, hash_params):
 
 # -------------------------------------------------------------------------------------- MLP ----
 @pytest.mark.parametrize("nh", [0, 1])
-@pytest.mark.parametrize("impl", ["v0", None])
+@pytest.mark.parametrize("impl", ["v0", "tc"])
 def test_mlp_fwd_bwd(oracle, nh, impl):
     from f2nerf_b200 import ops
     rng = np.random.default_rng(21 + nh)

@@ -26,7 +26,8 @@ N_RAYS = 512
 def ref():
     if not os.path.exists(DRV):
         pytest.skip("oracle/_ref/ref_driver not built")
-    out = os.path.join(ROOT, "gpurun_out", "ref_dump")
+    out = "/tmp/f2b_ref_dump"                                   # large (full 64 MB table gradient): not under gpurun_out
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     r = subprocess.run([DRV, os.path.join(ROOT, "oracle", "ref_config_ngp_fox.yaml"), out, str(N_RAYS), "0", "1"], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     open(os.path.join(ROOT, "gpurun_out", "ref_driver.log"), "w").write(r.stdout[-20000:] + "\n--- stderr ---\n" + r.stderr[-20000:])
