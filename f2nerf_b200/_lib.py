@@ -51,6 +51,7 @@ SIGNATURES = {
     "f2b_mlp_bwd_v0": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_tc": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_bwd_tc": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_field_fwd": [_P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P],
     "f2b_set_mlp_impl": [c_int],
     "f2b_get_mlp_impl": [],
     "f2b_cast_f32_to_f16": [_P, _P, c_i64, c_float, _P],

@@ -4,12 +4,30 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+#ifndef F2B_TC_BWD_DEFAULT
+#define F2B_TC_BWD_DEFAULT 0   // flipped to 1 once mlp_tc_bwd.cu is validated on hardware
+#endif
+
 extern "C" int f2b_mlp_fwd_v0(const void*, const void*, int, int, void*, void*, void*);
 extern "C" int f2b_mlp_bwd_v0(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
 #ifdef F2B_HAVE_TC
 extern "C" int f2b_mlp_fwd_tc(const void*, const void*, int, int, void*, void*, void*);
 extern "C" int f2b_mlp_bwd_tc(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
 #endif
+
+static int g_mlp_bwd_impl = -1;
+static int mlp_bwd_impl() {          // backward implementation follows F2B_MLP_BWD_IMPL, else the forward choice
+  if (g_mlp_bwd_impl < 0) {
+    const char* e = getenv("F2B_MLP_BWD_IMPL");
+#ifdef F2B_HAVE_TC
+    g_mlp_bwd_impl = e ? atoi(e) : F2B_TC_BWD_DEFAULT;
+#else
+    g_mlp_bwd_impl = 0;
+    (void)e;
+#endif
+  }
+  return g_mlp_bwd_impl;
+}
 
 static int g_mlp_impl = -1;
 static int mlp_impl() {
@@ -30,6 +48,7 @@ extern "C" int f2b_set_mlp_impl(int impl) {
   if (impl != 0) { f2b::set_error("f2b_set_mlp_impl: tcgen05 path not built"); return F2B_EUNSUPPORTED; }
 #endif
   g_mlp_impl = impl;
+  g_mlp_bwd_impl = impl ? F2B_TC_BWD_DEFAULT : 0;
   return F2B_OK;
 }
 extern "C" int f2b_get_mlp_impl(void) { return mlp_impl(); }
@@ -45,7 +64,7 @@ extern "C" int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void*
                            const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
                            float* dparams_f32, void* stream) {
 #ifdef F2B_HAVE_TC
-  if (mlp_impl() == 1) return f2b_mlp_bwd_tc(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
+  if (mlp_bwd_impl() == 1) return f2b_mlp_bwd_tc(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 #endif
   return f2b_mlp_bwd_v0(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 }

@@ -196,8 +196,6 @@ mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ para
 
 using namespace f2b;
 
-extern "C" int f2b_mlp_bwd_v0(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
-
 extern "C" int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
                               void* out_f16, void* hidden_save_f16, void* stream) {
   if (n_pts <= 0) return F2B_OK;
@@ -218,12 +216,3 @@ extern "C" int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_
   }
   return check_launch("f2b_mlp_fwd(tcgen05)");
 }
-
-// backward on tensor cores: see mlp_tc_bwd.cu once validated; until then the CUDA-core twin.
-#ifndef F2B_HAVE_TC_BWD
-extern "C" int f2b_mlp_bwd_tc(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
-                              const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
-                              float* dparams_f32, void* stream) {
-  return f2b_mlp_bwd_v0(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
-}
-#endif

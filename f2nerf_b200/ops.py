@@ -90,6 +90,18 @@ def hash_bwd(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, 
     return grad_table
 
 
+def field_fwd(table_f16, prim_pool, bias_pool, n_volumes, local_size, params_f16, pts, vol, vol_stride=1, logit_only=False,
+              save=False):
+    """Fused hash encode + tcgen05 field MLP.  -> (out [n] or [n,16] fp32, feat16 | None, hidden | None)."""
+    n = pts.shape[0]
+    out = dev_empty((n,) if logit_only else (n, 16), F32, pts)
+    feat = dev_empty((n, 32), F16, pts) if (save and not logit_only) else None
+    hidden = dev_empty((1, n, 64), F16, pts) if (save and not logit_only) else None
+    call("f2b_field_fwd", table_f16, prim_pool, bias_pool, int(n_volumes), int(local_size), params_f16, pts, vol,
+         int(vol_stride), n, int(bool(logit_only)), out, feat, hidden, stream())
+    return out, feat, hidden
+
+
 def mlp_fwd(x_f16, params_f16, n_hidden_matmuls, save_hidden=False, impl=None):
     n = x_f16.shape[0]
     out = dev_empty((n, 16), F16, x_f16)

@@ -138,7 +138,7 @@ class _RenderFunction(torch.autograd.Function):
         sparams16 = ops.cast_f32_to_f16(shader_params)
         scene_feat, feat16, f_hidden = field_forward(field, table16, fparams16, q_pts, q_anchors, 1, save=grad_on)
         emb = app_emb if pt_emb_idx is not None else None
-        mlp_in = ops.shader_prep(scene_feat, es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
+        mlp_in = ops.shader_prep(scene_feat[:n_kept], es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
             torch.empty((0, 32), dtype=torch.float16, device=bg.device)
         raw, s_hidden = ops.mlp_fwd(mlp_in, sparams16, shader.mlp_.n_hidden_matmuls, save_hidden=grad_on)
         rgb = ops.shader_act(raw)

@@ -118,6 +118,16 @@ int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_sav
 int f2b_cast_f32_to_f16(const float* src, void* dst, int64_t n, float scale, void* stream);
 int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
 
+/* Fused Hash3DAnchored::AnchoredQuery (Hash3DAnchored.cpp:84-99): hash encode + tcgen05 MLP(32->64->16) in one
+ * kernel; the encoded features reach HBM only through feat_save (backward needs them).
+ * logit_only != 0: the no-grad early-stop pass — out is [P] fp32 (channel 0 only), no saves.
+ * otherwise out is [P,16] fp32 (fp16-rounded values, as TCNNWP::Query returns); feat_save [P,32] fp16 and
+ * hidden_save [P,64] fp16 are optional. */
+int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
+                  int local_size, const void* mlp_params_f16, const float* pts, const int* vol, int vol_stride,
+                  int n_pts, int logit_only, float* out_f32, void* feat_save_f16, void* hidden_save_f16,
+                  void* stream);
+
 /* Implementation selection for f2b_mlp_fwd / f2b_mlp_bwd: 1 = tcgen05/TMEM kernels (default when
  * built), 0 = CUDA-core twin (validation).  Env F2B_MLP_IMPL overrides the default. */
 int f2b_set_mlp_impl(int impl);

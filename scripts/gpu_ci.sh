@@ -14,3 +14,7 @@ fi
 F2B_MLP_IMPL=$IMPL timeout 500 python bench.py --steps ${STEPS:-5} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 du -sh gpurun_out
+if [ "${NCU:-0}" = "1" ]; then
+  F2B_MLP_IMPL=$IMPL timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-gpu > gpurun_out/bench_ncu.log 2>&1
+  tail -n 3 gpurun_out/bench_ncu.log | cut -c1-300; wc -l gpurun_out/launches.csv
+fi

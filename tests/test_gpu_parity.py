@@ -163,7 +163,9 @@ def test_mlp_fwd_bwd(oracle, nh, impl):
     params = (oracle.mlp_init(32, nh) * 2).astype(np.float16)
     ref_out, ref_hid = oracle.mlp_fwd(x, params, nh, save_hidden=True)
     out, hid = ops.mlp_fwd(T(x), T(params), nh, save_hidden=True, impl=impl)
-    assert half_ulps(N(hid).astype(np.float32), ref_hid.astype(np.float32)) <= 2.0
+    assert half_ulps(N(hid)[0].astype(np.float32), ref_hid[0].astype(np.float32)) <= 2.0      # first layer: same operands
+    if nh:   # second layer sees first-layer outputs that may differ by an ulp: compare at the tensor's scale
+        assert_close(N(hid)[1].astype(np.float32), ref_hid[1].astype(np.float32), rtol=4e-3, atol_frac=2e-3, name="hidden 1")
     assert_close(N(out).astype(np.float32), ref_out.astype(np.float32), rtol=2e-3, atol_frac=1e-3, name="mlp out")
     # backward on the ORACLE's saved activations so both sides see identical operands
     dout = (rng.standard_normal((n, 16)) * 0.1).astype(np.float16)
@@ -171,6 +173,23 @@ def test_mlp_fwd_bwd(oracle, nh, impl):
     din, dp = ops.mlp_bwd(T(dout), T(x), T(ref_hid), T(params), nh, need_din=True, impl=impl)
     assert_close(N(din).astype(np.float32), rdin.astype(np.float32), rtol=4e-3, atol_frac=2e-3, name="mlp din")
     assert_close(N(dp), rdp, rtol=2e-3, atol_frac=2e-3, name="mlp dparams")
+
+
+def test_fused_field_matches_unfused(scene, oracle, hash_params):
+    """f2b_field_fwd (encode fused into the tcgen05 MLP) == f2b_hash_fwd -> f2b_mlp_fwd_tc, bit for bit."""
+    from f2nerf_b200 import ops
+    s = sample_points(scene, oracle, 100)
+    hp = hash_params
+    params = T((oracle.mlp_init(32, 0) * 3).astype(np.float16))
+    tab, prim, bias, pts, anc = T(hp["table"]), T(hp["prim"]), T(hp["bias"]), T(s["pts"]), T(s["anchors"])
+    feat = ops.hash_fwd(tab, prim, bias, hp["V"], hp["local_size"], pts, anc, 3)
+    out16, hid = ops.mlp_fwd(feat, params, 0, save_hidden=True, impl="tc")
+    out, f2, h2 = ops.field_fwd(tab, prim, bias, hp["V"], hp["local_size"], params, pts, anc, 3, save=True)
+    np.testing.assert_array_equal(N(f2).view(np.uint16), N(feat).view(np.uint16))
+    np.testing.assert_array_equal(N(h2).view(np.uint16), N(hid).view(np.uint16))
+    np.testing.assert_array_equal(N(out), N(out16).astype(np.float32))
+    logit, _, _ = ops.field_fwd(tab, prim, bias, hp["V"], hp["local_size"], params, pts, anc, 3, logit_only=True)
+    np.testing.assert_array_equal(N(logit), N(out)[:, 0])
 
 
 def test_mlp_init_matches_tcnn_stream(oracle):
@@ -282,6 +301,7 @@ def test_composite_fwd_bwd(scene, oracle):
 
 def test_composite_bwd_against_autograd(scene, oracle):
     """The oracle's analytic backward itself, checked against autograd of a plain torch fp64 composite."""
+    from f2nerf_b200 import CustomOps
     s, feat, rgb, bg = composite_inputs(scene, oracle, n_rays=8, seed=49)
     b = s["bounds"]
     x = torch.tensor(feat[:, 0], dtype=torch.float64, requires_grad=True)
@@ -292,7 +312,7 @@ def test_composite_bwd_against_autograd(scene, oracle):
     dc, dd, dz = rng.standard_normal((8, 3)), rng.standard_normal(8), rng.standard_normal(8)
     for r in range(8):
         sl = slice(b[r, 0], b[r, 1])
-        tau = torch.exp(x[sl] - 3) * dt[sl]
+        tau = CustomOps.TruncExp.apply(x[sl] - 3) * dt[sl]          # exp forward, exponent clamped to <= 5 backward
         A = torch.cumsum(tau, 0) - tau
         w = torch.exp(-A) * (1 - torch.exp(-tau))
         lt = torch.exp(-tau.sum())
@@ -350,8 +370,8 @@ def test_octree_votes_bit_exact(scene, oracle):
     w, a, keep, nb, tot = oracle.early_stop(feat, 16, s["dt"], s["bounds"])
     n_nodes = scene["nodes"].size // 64
     rng = np.random.default_rng(2)
-    sw0 = rng.integers(-3, 1200, n_nodes).astype(np.int32)       # some stats near zero so pruning triggers
-    sa0 = rng.integers(-3, 1200, n_nodes).astype(np.int32)
+    sw0 = rng.integers(-3, 4, n_nodes).astype(np.int32)          # stats near zero: visited-but-empty nodes get pruned
+    sa0 = rng.integers(-3, 4, n_nodes).astype(np.int32)
     # oracle
     vc = np.zeros(n_nodes, np.int32)
     vw, va, mk = oracle.mark_visit(s["bounds"], s["anchors"].reshape(-1)[1:].copy(), 3, w, a, n_nodes, vc)
