@@ -1,0 +1,103 @@
+"""Pins the CPU oracle against golden vectors produced by the REFERENCE ITSELF.
+
+tests/golden/ref_ngp_fox.npz was written by oracle/make_golden.py, which runs the unmodified
+Totoro97/f2-nerf (+ tiny-cuda-nn) operators (oracle/_ref/ref_driver) on a B200 with the reference's own
+ngp_fox octree and cameras.  CPU-only: runs in the `-m "not gpu"` suite.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "ref_ngp_fox.npz")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(GOLD), reason="golden fixture not generated yet (oracle/make_golden.py)")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(GOLD))
+
+
+def scalars(g):
+    sc = g["scalars"]
+    return dict(near=float(sc[0]), sample_l=float(sc[1]), scale_by_dis=bool(sc[2]), max_hits=int(sc[3]), V=int(sc[4]),
+                pool=int(sc[5]), n_img=int(sc[6]), n_rays=int(sc[7]))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_search_order_and_struct_sizes(g):
+    assert g["tree_nodes"].size % 64 == 0 and g["pers_trans"].size % 544 == 0 and g["edge_pool"].size % 64 == 0
+    want = [((~st) & 7) ^ (((k & 1) << 2) | (k & 2) | ((k >> 2) & 1)) for st in range(8) for k in range(8)]
+    np.testing.assert_array_equal(g["search_order"].astype(int), want)       # the closed form the kernels use
+
+
+def test_tcnn_param_init(g, oracle):
+    np.testing.assert_array_equal(oracle.mlp_init(32, 1), g["shader_mlp_params"])
+    np.testing.assert_array_equal(oracle.mlp_init(32, 0) * np.float32(4), g["field_mlp_params"])
+
+
+@pytest.mark.parametrize("mode", ["val", "train"])
+def test_sampler_bit_exact_vs_reference(g, oracle, mode):
+    s = scalars(g)
+    n = s["n_rays"]
+    noise = np.ones(1024 + n + 10, np.float32) if mode == "val" else g["train_noise"]
+    got = oracle.sampler(g["tree_nodes"], g["pers_trans"], g["rays_o"], g["rays_d_normed"], noise, s["near"], 1e8,
+                         s["sample_l"], s["scale_by_dis"], s["max_hits"])
+    np.testing.assert_array_equal(got["bounds"], g[f"{mode}_bounds"])
+    np.testing.assert_array_equal(got["anchors"][:, :2], g[f"{mode}_anchors"])
+    for k in ("t", "dt", "pts"):
+        np.testing.assert_array_equal(bits(got[k]), bits(g[f"{mode}_{k}"]), err_msg=k)
+    if mode == "val":
+        np.testing.assert_array_equal(bits(got["dirs"]), bits(g["val_dirs"]))
+        np.testing.assert_array_equal(bits(got["first_oct_dis"]), bits(g["val_first_oct_dis"]))
+    else:
+        np.testing.assert_array_equal(bits(got["first_oct_dis"]), bits(g["train_first_oct_dis"]))
+
+
+def test_edge_samples_feed_reference_edge_feats(g, oracle):
+    pts, idx = oracle.edge_samples(g["edge_pool"], g["pers_trans"], g["train_edge_idx"], g["train_edge_coord"])
+    assert np.isfinite(pts).all() and idx.min() >= 0 and idx.max() < scalars(g)["V"]
+
+
+def test_field_and_shader_vs_tcnn(g, oracle):
+    """hash encode (exact arithmetic) + MLP: tcnn accumulates in fp16, so agreement is at fp16 resolution."""
+    s = scalars(g)
+    gen = torch.Generator().manual_seed(1234)
+    table = (torch.rand((s["pool"], 2), generator=gen) * 2. - 1.).numpy().astype(np.float16)
+    local = ((s["pool"] // 16) >> 4) << 4
+    feat = oracle.hash_fwd(table, g["prim_pool"], g["bias_pool"], s["V"], local, g["level_scales"], g["val_pts"],
+                           np.ascontiguousarray(g["val_anchors"][:, 0]), 1)
+    out, _ = oracle.mlp_fwd(feat, g["field_mlp_params"].astype(np.float16), 0)
+    ref = g["val_scene_feat"].astype(np.float32)
+    err = np.abs(out.astype(np.float32) - ref)
+    scale = np.abs(ref).max()
+    assert np.median(err) <= 2e-3 * scale and err.max() <= 0.03 * scale, (np.median(err), err.max(), scale)
+    shading = ref.copy(); shading[:, 0] = 1.0
+    mlp_in = oracle.shader_prep(shading, g["val_dirs"])
+    raw, _ = oracle.mlp_fwd(mlp_in, g["shader_mlp_params"].astype(np.float16), 1)
+    rgb = oracle.shader_act(raw)
+    assert np.abs(rgb - g["val_rgb"]).max() <= 0.02 and np.median(np.abs(rgb - g["val_rgb"])) <= 2e-3
+
+
+def test_early_stop_and_composite_vs_reference(g, oracle):
+    """Composite restatement on the reference's own per-sample features / colours (VALIDATE: bg = 0.5)."""
+    ref_feat = g["val_scene_feat"].astype(np.float32)
+    w0, a0, keep, nb, tot = oracle.early_stop(ref_feat, 16, g["val_dt"], g["val_bounds"])
+    theirs = g["val_idx_start_end"]
+    cnt_m, cnt_t = nb[:, 1] - nb[:, 0], theirs[:, 1] - theirs[:, 0]
+    assert (cnt_m != cnt_t).sum() <= 1 and np.abs(cnt_m - cnt_t).max() <= 1      # T > 1e-4 straddlers only (libm vs MUFU exp)
+    if not np.array_equal(nb, theirs):
+        pytest.skip("a threshold-straddling sample flipped; composite comparison needs identical masks")
+    m = keep.astype(bool)
+    bg = np.full((theirs.shape[0], 3), 0.5, np.float32)
+    colors, disp, depth, w = oracle.composite_fwd(np.ascontiguousarray(ref_feat[m]), 16, np.ascontiguousarray(g["val_rgb"][m]),
+                                                  np.ascontiguousarray(g["val_dt"][m]), np.ascontiguousarray(g["val_t"][m]), nb, bg)
+    for mine, name in ((w, "val_weights"), (colors, "val_colors"), (disp, "val_disparity"), (depth, "val_depth")):
+        ref = g[name].reshape(mine.shape)
+        np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-4 * max(np.abs(ref).max(), 1e-6), err_msg=name)
