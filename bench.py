@@ -41,33 +41,40 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons during the timed region, sampled in-process through NVML (no nvidia-smi
+    subprocesses: they stall kernel launches for tens of ms each)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.err = index, [], False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                time.sleep(0.05)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)[:120]
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        import pynvml as nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_mhz), "reasons": [k for k, v in names.items() if bits & v],
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows)}
 
 
 def build_problem(rank, n_rays, log2_table, device):
@@ -110,7 +117,7 @@ def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None):
 
 
 ALGO_BYTES = {  # algorithmic bytes per unit (sample) at the operator boundary â€” DESIGN.md "roofline accounting"
-    "f2b_hash_fwd": 16 + 512 + 64, "f2b_hash_bwd": 16 + 64 + 512, "f2b_sampler_fill": 44, "f2b_sampler_count": 0,
+    "f2b_field_fwd": 16 + 512 + 64, "f2b_hash_fwd": 16 + 512 + 64, "f2b_hash_bwd": 16 + 64 + 512, "f2b_sampler_fill": 44, "f2b_sampler_count": 0,
     "f2b_composite_fwd": 28, "f2b_composite_bwd": 24 + 16 + 16, "f2b_early_stop": 8 + 9, "f2b_compact_samples": 88,
     "f2b_shader_prep": 64 + 12 + 64, "f2b_shader_act": 32 + 12, "f2b_cast_f16_to_f32": 6, "f2b_cast_f32_to_f16": 6,
 }
@@ -118,7 +125,7 @@ ALGO_BYTES = {  # algorithmic bytes per unit (sample) at the operator boundary â
 
 def unit_count(name, ints):
     """number of samples (units) a traced call processed, from its integer arguments."""
-    pos = {"f2b_hash_fwd": 3, "f2b_hash_bwd": 3, "f2b_mlp_fwd": 1, "f2b_mlp_bwd": 1, "f2b_shader_prep": 0,
+    pos = {"f2b_field_fwd": 3, "f2b_hash_fwd": 3, "f2b_hash_bwd": 3, "f2b_mlp_fwd": 1, "f2b_mlp_bwd": 1, "f2b_shader_prep": 0,
            "f2b_shader_act": 0, "f2b_shader_act_bwd": 0, "f2b_shader_prep_bwd": 0, "f2b_cast_f16_to_f32": 0,
            "f2b_cast_f32_to_f16": 0, "f2b_table_to_half": 0}
     if name in pos and len(ints) > pos[name]:

@@ -36,7 +36,7 @@ _P = c_void_p
 SIGNATURES = {
     "f2b_abi_version": [],
     "f2b_device_info": [_P, _P],
-    "f2b_sampler_count": [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_int, c_int, _P, _P, _P, _P],
+    "f2b_sampler_count": [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_int, c_int, c_int, _P, _P, _P, _P],
     "f2b_sampler_fill": [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_edge_samples": [_P, _P, _P, _P, c_int, _P, _P, _P],
     "f2b_oct_mark_visit": [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
@@ -61,7 +61,7 @@ SIGNATURES = {
     "f2b_shader_prep": [_P, _P, _P, _P, c_int, _P, _P],
     "f2b_shader_act": [_P, c_int, _P, _P],
     "f2b_shader_act_bwd": [_P, _P, c_int, c_float, _P, _P],
-    "f2b_shader_prep_bwd": [_P, _P, c_int, c_float, c_int, _P, _P, _P],
+    "f2b_shader_prep_bwd": [_P, _P, _P, c_int, c_float, _P, _P, _P],
     "f2b_early_stop": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
     "f2b_compact_samples": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_composite_fwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],

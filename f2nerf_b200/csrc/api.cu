@@ -5,7 +5,7 @@
 #include <stdlib.h>
 
 #ifndef F2B_TC_BWD_DEFAULT
-#define F2B_TC_BWD_DEFAULT 0   // flipped to 1 once mlp_tc_bwd.cu is validated on hardware
+#define F2B_TC_BWD_DEFAULT 1   // mlp_tc_bwd.cu validated on B200 (tests/test_gpu_parity.py::test_mlp_fwd_bwd[tc-*])
 #endif
 
 extern "C" int f2b_mlp_fwd_v0(const void*, const void*, int, int, void*, void*, void*);

@@ -59,13 +59,23 @@ using namespace f2b;
 extern "C" const char* f2b_last_error(void) { return g_err; }
 extern "C" int f2b_abi_version(void) { return 1; }
 
+// per-device cache: cudaGetDeviceProperties costs milliseconds and must not sit on the launch path
 extern "C" int f2b_device_info(int* sm_count, int* l2_bytes) {
+  static int s_sm[64], s_l2[64];
+  static bool s_have[64] = {false};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("f2b_device_info: no CUDA device"); return F2B_ECUDA; }
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { set_error("f2b_device_info: query failed"); return F2B_ECUDA; }
-  if (sm_count) *sm_count = p.multiProcessorCount;
-  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("f2b_device_info: no CUDA device"); return F2B_ECUDA; }
+  if (!s_have[dev]) {
+    int sm = 0, l2 = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) != cudaSuccess) {
+      set_error("f2b_device_info: query failed");
+      return F2B_ECUDA;
+    }
+    s_sm[dev] = sm; s_l2[dev] = l2; s_have[dev] = true;
+  }
+  if (sm_count) *sm_count = s_sm[dev];
+  if (l2_bytes) *l2_bytes = s_l2[dev];
   return F2B_OK;
 }
 

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kRaysPerBlock* kLanesPerRay)
 march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ trans,
              const float* __restrict__ rays_o, const float* __restrict__ rays_d,
              const float* __restrict__ rays_noise, int n_rays, float near0, float far0,
-             float sample_l, int scale_by_dis, int max_hits,
+             float sample_l, int scale_by_dis, int max_hits, int count_all_hits,
              int* __restrict__ ray_counts,            // count pass out
              int* __restrict__ total_hits,            // count pass out (atomic)
              const int* __restrict__ bounds,          // fill pass in
@@ -191,13 +191,18 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
   if (FILL && active && sub == 0) first_oct_dis[ray] = have ? hit.near : 1e9f;
 
   int k = 0;
-  if (have && cap > 0) {
+  {
     float t = hit.near, far = hit.far;
     int cur_node = hit.node, cur_trans = hit.trans_idx, loaded_trans = -1;
     bool first = true;
     TransSlice ts;
     float rclip = 1.f;
-    while (k < cap && have) {
+    // Warp-uniform trip count: every lane stays in the loop until the slowest ray of the warp is done and
+    // the warp re-converges at the __any_sync each step, so the 8 ray-groups execute the step together
+    // (a data-dependent `while (k < cap && have)` lets the groups drift apart and serialises them 8x).
+    bool running = have && cap > 0;
+    while (__any_sync(0xffffffffu, running)) {
+      if (running) {
       if (cur_trans != loaded_trans) {
         load_slice(trans + cur_trans, sub, ts);
         loaded_trans = cur_trans;
@@ -270,10 +275,14 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
       }
       t = tn;
       first = false;
+      running = (k < cap) && have;
+      }
     }
   }
   if (!FILL) {
-    while (next_hit(dfs, nodes, o, d, near0, far0, hit)) {}   // exhaust: total hit count (:353,378)
+    if (count_all_hits) {                                      // exact n_all_oct_intersect (:353,378), informational EMA only
+      while (next_hit(dfs, nodes, o, d, near0, far0, hit)) {}
+    }
     if (active && sub == 0) {
       ray_counts[ray] = k;
       if (dfs.n_hits) atomicAdd(total_hits, dfs.n_hits);
@@ -410,8 +419,8 @@ using namespace f2b;
 extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
                                  const float* rays_o, const float* rays_d, const float* rays_noise,
                                  int n_rays, float near, float far, float sample_l, int scale_by_dis,
-                                 int max_oct_intersect_per_ray, int* ray_counts, int* pts_idx_bounds,
-                                 int* totals, void* stream) {
+                                 int max_oct_intersect_per_ray, int count_all_hits, int* ray_counts,
+                                 int* pts_idx_bounds, int* totals, void* stream) {
   F2B_REQUIRE(n_rays >= 0 && n_nodes > 0 && n_trans >= 0, "f2b_sampler_count: bad sizes");
   F2B_REQUIRE(totals, "f2b_sampler_count: null totals");
   cudaStream_t st = as_stream(stream);
@@ -421,7 +430,7 @@ extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void
               "f2b_sampler_count: null pointer");
   march_kernel<false><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
-      far, sample_l, scale_by_dis, max_oct_intersect_per_ray, ray_counts, totals + 1, nullptr, nullptr,
+      far, sample_l, scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, nullptr,
       nullptr, nullptr, nullptr, nullptr, nullptr);
   scan_counts_kernel<<<1, 1024, 0, st>>>(ray_counts, n_rays, pts_idx_bounds, totals);
   return check_launch("f2b_sampler_count");
@@ -438,7 +447,7 @@ extern "C" int f2b_sampler_fill(const void* tree_nodes, int n_nodes, const void*
   F2B_REQUIRE(tree_nodes && trans && pts_idx_bounds && first_oct_dis, "f2b_sampler_fill: null pointer");
   march_kernel<true><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, as_stream(stream)>>>(
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
-      far, sample_l, scale_by_dis, max_oct_intersect_per_ray, nullptr, nullptr, pts_idx_bounds, pts,
+      far, sample_l, scale_by_dis, max_oct_intersect_per_ray, 0, nullptr, nullptr, pts_idx_bounds, pts,
       dirs, dt, t, anchors, first_oct_dis);
   return check_launch("f2b_sampler_fill");
 }

@@ -118,46 +118,52 @@ __global__ void shader_act_bwd_kernel(const __half* __restrict__ raw, const floa
   dst[1] = *reinterpret_cast<uint4*>(h + 4);
 }
 
-// Backward of the input assembly: d scene_feat[:,1:16] = d mlp_in[:,1:16] / loss_scale (channel 0 of
-// scene_feat is the density logit, filled by the composite backward), and the appearance-embedding
-// gradient d app_emb[cam] += d mlp_in[:,0:16] (ScatterAddFuncBackwardBlock, Scatter.cu:23-40) via a
-// block-local shared-memory histogram followed by one atomicAdd per (camera, channel) per block.
+// Backward of the input assembly, one warp per ray: d scene_feat[:,1:16] = d mlp_in[:,1:16] / loss_scale
+// (channel 0 of scene_feat is the density logit, filled by the composite backward) and the appearance-
+// embedding gradient d app_emb[cam(ray)] += sum over the ray's samples of d mlp_in[:,0:16]
+// (ScatterAddFuncBackwardBlock, Scatter.cu:23-40 — there a dense [n_emb x n_blocks] compare-and-sum).  The
+// camera index is constant along a ray, so the sum is a register accumulation + one warp reduction + 16
+// atomicAdds per ray instead of one atomic per sample and channel.
 __global__ void __launch_bounds__(256)
-shader_prep_bwd_kernel(const __half* __restrict__ d_mlp_in, const int* __restrict__ pt_emb_idx, int n,
-                       float inv_loss_scale, int n_emb, float* __restrict__ d_scene_feat,
-                       float* __restrict__ d_app_emb) {
-  extern __shared__ float s_emb[];   // [n_emb][16] when d_app_emb
-  if (d_app_emb) {
-    for (int k = threadIdx.x; k < n_emb * 16; k += blockDim.x) s_emb[k] = 0.f;
-    __syncthreads();
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + blockDim.x - 1) / blockDim.x) * blockDim.x;
-       i += gridDim.x * blockDim.x) {
-    if (i < n) {
-      const uint4* s = reinterpret_cast<const uint4*>(d_mlp_in + size_t(i) * 32);
-      float g[16];
+shader_prep_bwd_kernel(const __half* __restrict__ d_mlp_in, const int* __restrict__ bounds,
+                       const int* __restrict__ emb_idx, int n_rays, float inv_loss_scale,
+                       float* __restrict__ d_scene_feat, float* __restrict__ d_app_emb) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= n_rays) return;
+  const int beg = bounds[2 * ray], end = bounds[2 * ray + 1];
+  float acc[16];
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint4 r = s[q];
-        const __half2* h = reinterpret_cast<const __half2*>(&r);
+  for (int k = 0; k < 16; k++) acc[k] = 0.f;
+  for (int i = beg + lane; i < end; i += 32) {
+    const uint4* s = reinterpret_cast<const uint4*>(d_mlp_in + size_t(i) * 32);
+    float g[16];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); g[8 * q + 2 * k] = f.x * inv_loss_scale; g[8 * q + 2 * k + 1] = f.y * inv_loss_scale; }
-      }
-      float* dst = d_scene_feat + size_t(i) * 16;
+    for (int q = 0; q < 2; q++) {
+      const uint4 r = __ldg(s + q);
+      const __half2* h = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-      for (int k = 1; k < 16; k++) dst[k] = g[k];
-      if (d_app_emb) {
-        float* e = s_emb + pt_emb_idx[i] * 16;
-#pragma unroll
-        for (int k = 0; k < 16; k++) atomicAdd(e + k, g[k]);
-      }
+      for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); g[8 * q + 2 * k] = f.x * inv_loss_scale; g[8 * q + 2 * k + 1] = f.y * inv_loss_scale; }
     }
+    float* dst = d_scene_feat + size_t(i) * 16;
+#pragma unroll
+    for (int k = 1; k < 16; k++) dst[k] = g[k];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] += g[k];
   }
   if (d_app_emb) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < n_emb * 16; k += blockDim.x) {
-      const float v = s_emb[k];
-      if (v != 0.f) atomicAdd(d_app_emb + k, v);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      float v = acc[k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[k] = v;
+    }
+    if (lane < 16 && end > beg) {
+      float v = acc[0];
+#pragma unroll
+      for (int k = 1; k < 16; k++) v = (lane == k) ? acc[k] : v;
+      atomicAdd(d_app_emb + size_t(emb_idx[ray]) * 16 + lane, v);
     }
   }
 }
@@ -203,17 +209,12 @@ extern "C" int f2b_shader_act_bwd(const void* raw_out_f16, const float* d_rgb, i
   return check_launch("f2b_shader_act_bwd");
 }
 
-extern "C" int f2b_shader_prep_bwd(const void* d_mlp_in_f16, const int* pt_emb_idx, int n_pts, float inv_loss_scale,
-                                   int n_emb, float* d_scene_feat, float* d_app_emb, void* stream) {
-  if (n_pts <= 0) return F2B_OK;
-  F2B_REQUIRE(d_mlp_in_f16 && d_scene_feat, "f2b_shader_prep_bwd: null pointer");
-  F2B_REQUIRE(!d_app_emb || (pt_emb_idx && n_emb > 0 && n_emb * 16 * 4 <= 96 * 1024), "f2b_shader_prep_bwd: bad embedding args");
-  int sms = 148;
-  f2b_device_info(&sms, nullptr);
-  const int blocks = d_app_emb ? min(div_up(n_pts, 256), sms * 4) : div_up(n_pts, 256);
-  const size_t smem = d_app_emb ? size_t(n_emb) * 16 * sizeof(float) : 0;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(shader_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  shader_prep_bwd_kernel<<<blocks, 256, smem, as_stream(stream)>>>((const __half*)d_mlp_in_f16, pt_emb_idx, n_pts,
-                                                                  inv_loss_scale, n_emb, d_scene_feat, d_app_emb);
+extern "C" int f2b_shader_prep_bwd(const void* d_mlp_in_f16, const int* pts_idx_bounds, const int* emb_idx, int n_rays,
+                                   float inv_loss_scale, float* d_scene_feat, float* d_app_emb, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(d_mlp_in_f16 && pts_idx_bounds && d_scene_feat, "f2b_shader_prep_bwd: null pointer");
+  F2B_REQUIRE(!d_app_emb || emb_idx, "f2b_shader_prep_bwd: d_app_emb without emb_idx");
+  shader_prep_bwd_kernel<<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(
+      (const __half*)d_mlp_in_f16, pts_idx_bounds, emb_idx, n_rays, inv_loss_scale, d_scene_feat, d_app_emb);
   return check_launch("f2b_shader_prep_bwd");
 }

@@ -175,12 +175,21 @@ class Hash3DAnchored:
         self.mlp_.InitParams()
 
 
-def field_forward(field, table16, params16, points, anchors, anchor_stride, save):
-    """hash encode -> MLP; returns (out fp32 [n,16], feat16, hidden) (the latter two only when ``save``)."""
+def field_forward(field, table16, params16, points, anchors, anchor_stride, save, logit_only=False):
+    """hash encode -> MLP.  Returns (out, feat16, hidden); out is fp32 [n,16], or [n] (channel 0) when
+    ``logit_only``; feat16 / hidden only when ``save``.  With the tcgen05 MLP selected (default) this is ONE
+    fused kernel (f2b_field_fwd); with the CUDA-core twin it is encode + MLP + cast."""
+    from . import _lib
+    if _lib.lib.f2b_get_mlp_impl() == 1 and field.mlp_.n_hidden_matmuls == 0:
+        return ops.field_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, params16,
+                             points, anchors, anchor_stride, logit_only=logit_only, save=save)
     feat16 = ops.hash_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, points,
                           anchors, anchor_stride)
     out16, hidden = ops.mlp_fwd(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save)
-    return ops.cast_f16_to_f32(out16), (feat16 if save else None), hidden
+    out = ops.cast_f16_to_f32(out16)
+    if logit_only:
+        out = out[:, 0].contiguous()
+    return out, (feat16 if save else None), hidden
 
 
 def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidden, d_out_f32):

@@ -28,14 +28,14 @@ def dev_empty(shape, dtype, like):
 
 
 # ------------------------------------------------------------------ sampler ---------------------
-def sampler_count(tree_nodes, trans, rays_o, rays_d, noise, near, far, sample_l, scale_by_dis, max_hits):
+def sampler_count(tree_nodes, trans, rays_o, rays_d, noise, near, far, sample_l, scale_by_dis, max_hits, count_all_hits=True):
     R = rays_o.shape[0]
     counts = dev_empty((max(R, 1),), I32, rays_o)
     bounds = dev_empty((R, 2), I32, rays_o)
     totals = dev_empty((2,), I32, rays_o)
     call("f2b_sampler_count", tree_nodes, tree_nodes.numel() // 64, trans, trans.numel() // 544, rays_o, rays_d,
-         noise, R, float(near), float(far), float(sample_l), int(bool(scale_by_dis)), int(max_hits), counts, bounds,
-         totals, stream())
+         noise, R, float(near), float(far), float(sample_l), int(bool(scale_by_dis)), int(max_hits), int(bool(count_all_hits)),
+         counts, bounds, totals, stream())
     return bounds, totals
 
 
@@ -167,9 +167,8 @@ def shader_act_bwd(raw_f16, d_rgb, loss_scale):
     return out
 
 
-def shader_prep_bwd(d_mlp_in_f16, pt_emb_idx, inv_loss_scale, n_emb, d_scene_feat, d_app_emb):
-    n = d_mlp_in_f16.shape[0]
-    call("f2b_shader_prep_bwd", d_mlp_in_f16, pt_emb_idx, n, float(inv_loss_scale), int(n_emb), d_scene_feat,
+def shader_prep_bwd(d_mlp_in_f16, bounds, emb_idx, inv_loss_scale, d_scene_feat, d_app_emb):
+    call("f2b_shader_prep_bwd", d_mlp_in_f16, bounds, emb_idx, bounds.shape[0], float(inv_loss_scale), d_scene_feat,
          d_app_emb, stream())
 
 

@@ -77,8 +77,8 @@ class Renderer:
         with torch.no_grad():
             table16 = field.table_f16()
             fparams16 = field.mlp_.params_f16()
-            feat_all, _, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False)
-            weights0, alphas0, keep, new_bounds, total = ops.early_stop(feat_all, 16, sr.dt, sr.pts_idx_bounds)
+            logit_all, _, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False, logit_only=True)
+            weights0, alphas0, keep, new_bounds, total = ops.early_stop(logit_all, 1, sr.dt, sr.pts_idx_bounds)
             n_kept = int(total.item())                                               # sync 2
             if train:
                 sampler.UpdateOctNodes(sr, weights0, alphas0)
@@ -92,12 +92,13 @@ class Renderer:
                 q_anchors = torch.cat([anchors[:, 0], edge_anchors.reshape(N_EDGE_PTS * 2)], 0).contiguous()
             else:
                 q_pts, q_anchors = pts, anchors[:, 0].contiguous()
-            pt_emb_idx = None
+            pt_emb_idx = ray_emb_idx = None
             if train and self.use_app_emb_:
-                pt_emb_idx = ops.scatter_idx(n_kept, new_bounds, emb_idx.to(torch.int32).contiguous())
+                ray_emb_idx = emb_idx.to(torch.int32).contiguous()
+                pt_emb_idx = ops.scatter_idx(n_kept, new_bounds, ray_emb_idx)
 
         grad_on = torch.is_grad_enabled() and train
-        args = (self, es, q_pts, q_anchors, pt_emb_idx, bg, table16, n_kept, grad_on)
+        args = (self, es, q_pts, q_anchors, pt_emb_idx, ray_emb_idx, bg, table16, n_kept, grad_on)
         colors, disparity, depth, weights, edge_feats = _RenderFunction.apply(
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, *args)
         if not train:
@@ -131,8 +132,8 @@ class _RenderFunction(torch.autograd.Function):
     """Second half of Renderer::Render (Renderer.cpp:152-208) with its whole backward."""
 
     @staticmethod
-    def forward(ctx, feat_pool, field_params, shader_params, app_emb, renderer, es, q_pts, q_anchors, pt_emb_idx, bg,
-                table16, n_kept, grad_on):
+    def forward(ctx, feat_pool, field_params, shader_params, app_emb, renderer, es, q_pts, q_anchors, pt_emb_idx,
+                ray_emb_idx, bg, table16, n_kept, grad_on):
         field, shader = renderer.scene_field_, renderer.shader_
         fparams16 = ops.cast_f32_to_f16(field_params)
         sparams16 = ops.cast_f32_to_f16(shader_params)
@@ -145,7 +146,7 @@ class _RenderFunction(torch.autograd.Function):
         colors, disparity, depth, weights = ops.composite_fwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg)
         edge_feats = scene_feat[n_kept:].reshape(-1, 2, 16)
         ctx.renderer, ctx.es, ctx.n_kept = renderer, es, n_kept
-        ctx.pack = (fparams16, sparams16, q_pts, q_anchors, pt_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
+        ctx.pack = (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
                     s_hidden, rgb)
         ctx.gs_progress = renderer.global_data_pool_.gradient_scaling_progress_
         return colors, disparity, depth, weights, edge_feats
@@ -154,7 +155,7 @@ class _RenderFunction(torch.autograd.Function):
     def backward(ctx, d_colors, d_disp, d_depth, d_weights, d_edge):
         renderer, es, n_kept = ctx.renderer, ctx.es, ctx.n_kept
         field, shader, gdp = renderer.scene_field_, renderer.shader_, renderer.global_data_pool_
-        (fparams16, sparams16, q_pts, q_anchors, pt_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
+        (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
          rgb) = ctx.pack
         if feat16 is None:
             raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
@@ -176,14 +177,14 @@ class _RenderFunction(torch.autograd.Function):
         d_raw = ops.shader_act_bwd(raw, d_rgb, s_scale)
         d_in16, d_sparams = ops.mlp_bwd(d_raw, mlp_in, s_hidden, sparams16, shader.mlp_.n_hidden_matmuls, need_din=True)
         d_sparams = d_sparams / s_scale
-        d_app = torch.zeros_like(renderer.app_emb_) if pt_emb_idx is not None else None
-        ops.shader_prep_bwd(d_in16, pt_emb_idx, 1.0 / s_scale, renderer.app_emb_.shape[0], d_scene, d_app)
+        d_app = torch.zeros_like(renderer.app_emb_) if ray_emb_idx is not None else None
+        ops.shader_prep_bwd(d_in16, es.pts_idx_bounds, ray_emb_idx, 1.0 / s_scale, d_scene, d_app)
         # field: MLP -> hash scatter
         d_table, d_fparams = field_backward(field, fparams16, q_pts, q_anchors, 1, feat16, f_hidden, d_scene)
         # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
         bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
         renderer.nonfinite_flag_ = bad
-        return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None
+        return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None, None
 
 
 def check_backward_nan(renderer):

@@ -66,6 +66,7 @@ class PersSampler:
         self.global_near_, self.sample_l_, self.scale_by_dis_ = float(near), float(sample_l), bool(scale_by_dis)
         self.max_oct_intersect_per_ray_ = int(max_oct_intersect_per_ray)
         self.sub_div_milestones_ = []
+        self.exact_oct_stat_ = False         # True: run the traversal to exhaustion for the exact "OctSamples" log EMA
         self.vote_allreduce_ = None          # set by f2nerf_b200.dist.install_vote_sync under data parallelism
         global_data_pool.n_volumes_ = self.pers_trans_gpu_.numel() // 544
 
@@ -97,7 +98,7 @@ class PersSampler:
             rays_noise = self.make_noise(n_rays, rays_o.device)
         args = (self.tree_nodes_gpu_, self.pers_trans_gpu_, rays_o, rays_d, rays_noise, self.global_near_, 1e8,
                 self.sample_l_, self.scale_by_dis_, self.max_oct_intersect_per_ray_)
-        bounds, totals = ops.sampler_count(*args)
+        bounds, totals = ops.sampler_count(*args, count_all_hits=self.exact_oct_stat_)
         n_all_pts, n_all_oct = (int(v) for v in totals.tolist())            # the one sync
         if gdp.mode_ != VALIDATE and n_rays > 0:
             gdp.sampled_oct_per_ray_ = gdp.sampled_oct_per_ray_ * .9 + (n_all_oct / n_rays) * .1

@@ -29,7 +29,7 @@ SampleResultFlex B200Sampler::GetSamples(const Tensor& rays_o_raw, const Tensor&
   Tensor totals = torch::empty({2}, CUDAInt);
   F2B_CHECK(f2b_sampler_count(nodes.data_ptr(), nodes.numel() / 64, trans.data_ptr(), trans.numel() / 544,
                               rays_o.data_ptr<float>(), rays_d.data_ptr<float>(), noise.data_ptr<float>(), n_rays,
-                              global_near_, 1e8f, sample_l_, scale_by_dis_, max_oct_intersect_per_ray_,
+                              global_near_, 1e8f, sample_l_, scale_by_dis_, max_oct_intersect_per_ray_, /*count_all_hits=*/1,
                               counts.data_ptr<int>(), bounds.data_ptr<int>(), totals.data_ptr<int>(), cur_stream()));
   Tensor totals_cpu = totals.to(torch::kCPU);                           // the one host sync
   const int n_pts = totals_cpu[0].item<int>(), n_oct = totals_cpu[1].item<int>();

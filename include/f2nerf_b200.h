@@ -46,11 +46,13 @@ int  f2b_device_info(int* sm_count, int* l2_bytes);
  * rays_noise has F2B_MAX_SAMPLE_PER_RAY + n_rays + 10 floats, already scaled by fineness (:373-381).
  * ------------------------------------------------------------------------------------------ */
 /* Pass 1: per-ray sample counts -> exclusive/inclusive bounds (reference: cumsum at :395),
- * totals[0] = n_all_pts, totals[1] = n_all_oct_intersect (for the sampled_oct_per_ray EMA, :378). */
+ * totals[0] = n_all_pts, totals[1] = octree hits: with count_all_hits != 0 the exact n_all_oct_intersect of
+ * :353 (the traversal is run to exhaustion — only feeds the informational sampled_oct_per_ray EMA, :378),
+ * otherwise the hits the march actually consumed. */
 int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
                       const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
                       float near, float far, float sample_l, int scale_by_dis,
-                      int max_oct_intersect_per_ray,
+                      int max_oct_intersect_per_ray, int count_all_hits,
                       int* ray_counts /* [n_rays] caller-owned scratch */,
                       int* pts_idx_bounds /* [n_rays,2] out */, int* totals /* [2] out */,
                       void* stream);
@@ -159,12 +161,13 @@ int f2b_shader_act(const void* raw_out_f16 /* [P,16] */, int n_pts, float* rgb /
 /* Backward of the activation: d_raw[P,16] fp16 = loss_scale * d_rgb * sigmoid' (channels 3..15 zero). */
 int f2b_shader_act_bwd(const void* raw_out_f16, const float* d_rgb, int n_pts, float loss_scale,
                        void* d_raw_f16, void* stream);
-/* Backward of the input assembly: d_scene_feat[p,1:16] = d_mlp_in[p,1:16]*inv_loss_scale (column 0 is left
- * to the composite backward) and, when d_app_emb != NULL, d_app_emb[cam] += d_mlp_in[p,0:16]
+/* Backward of the input assembly (one warp per ray): d_scene_feat[p,1:16] = d_mlp_in[p,1:16]*inv_loss_scale
+ * (column 0 is left to the composite backward) and, when d_app_emb != NULL,
+ * d_app_emb[emb_idx[ray]] += sum over the ray's samples of d_mlp_in[p,0:16]*inv_loss_scale
  * (ScatterAddFuncBackwardBlock, Scatter.cu:23-40). */
-int f2b_shader_prep_bwd(const void* d_mlp_in_f16 /* [P,32] */, const int* pt_emb_idx, int n_pts,
-                        float inv_loss_scale, int n_emb, float* d_scene_feat /* [P,16] */,
-                        float* d_app_emb /* [n_emb,16] or NULL */, void* stream);
+int f2b_shader_prep_bwd(const void* d_mlp_in_f16 /* [P,32] */, const int* pts_idx_bounds /* [R,2] */,
+                        const int* emb_idx /* [R] or NULL */, int n_rays, float inv_loss_scale,
+                        float* d_scene_feat /* [P,16] */, float* d_app_emb /* [n_emb,16] or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Composite — replaces the Renderer::Render tail (src/Renderer/Renderer.cpp:107-150,196-208),

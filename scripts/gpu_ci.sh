@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, reference parity, sanitizer on the end-to-end step, bench.  Logs (small) -> gpurun_out/.
 mkdir -p gpurun_out
-IMPL=${IMPL:-0}
+IMPL=${IMPL:-1}
 echo "== gpu: $(nvidia-smi -L) / nproc $(nproc) / impl $IMPL"
 F2B_MLP_IMPL=$IMPL timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_ref_parity.py -p no:cacheprovider -k "not tc and not fused" > gpurun_out/pytest_gpu.log 2>&1
 tail -n 40 gpurun_out/pytest_gpu.log

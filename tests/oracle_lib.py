@@ -97,11 +97,11 @@ def hash_fwd(table_h, prim, bias, n_volumes, local_size, scales, pts, vol, vol_s
     return out.view(np.float16)
 
 
-def hash_bwd(prim, bias, n_volumes, local_size, scales, pts, vol, vol_stride, grad_feat, grad_mul, pool_size):
+def hash_bwd(prim, bias, n_volumes, local_size, scales, pts, vol, vol_stride, grad_feat, grad_mul, pool_size, half_products=False):
     g = np.zeros(pool_size * 2, np.float64)
     lib().orc_hash_bwd(_p(c(prim, np.int32)), _p(c(bias, np.float32)), I(n_volumes), I(local_size),
                        _p(c(scales, np.float32)), _p(c(pts, np.float32)), _p(c(vol, np.int32)), I(vol_stride),
-                       I(pts.shape[0]), _p(c(grad_feat, np.float32)), F(grad_mul), _p(g))
+                       I(pts.shape[0]), _p(c(grad_feat, np.float32)), F(grad_mul), I(int(half_products)), _p(g))
     return g.reshape(pool_size, 2)
 
 

@@ -100,5 +100,9 @@ def render_train(sc, rays_o, rays_dn, noise, bg, field, shader_params, app_emb=N
     out["grad_feat_pool"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
                                        np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32), 1.0 / LOSS_SCALE,
                                        field["table16"].shape[0])
+    # the same scatter with the reference's per-product fp16 rounding (Hash3DAnchored.cu:145-151) emulated
+    out["grad_feat_pool_half_products"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
+                                                     np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32),
+                                                     1.0 / LOSS_SCALE, field["table16"].shape[0], half_products=True)
     out["d_scene"] = d_scene
     return out

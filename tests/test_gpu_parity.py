@@ -227,18 +227,24 @@ def test_shader_prep_and_act(oracle):
 def test_shader_prep_bwd(oracle):
     from f2nerf_b200 import ops
     rng = np.random.default_rng(33)
-    n, n_emb = 5000, 42
+    n_emb = 42
+    lens = rng.integers(0, 200, 300).astype(np.int32); lens[5] = 0
+    bounds = np.stack([np.cumsum(lens) - lens, np.cumsum(lens)], -1).astype(np.int32)
+    n = int(lens.sum())
     g = (rng.standard_normal((n, 32)) * 4).astype(np.float16)
-    idx = rng.integers(0, n_emb, n).astype(np.int32)
+    ray_idx = rng.integers(0, n_emb, 300).astype(np.int32)
     d_scene = torch.full((n, 16), 7.0, device=DEV)
     d_app = torch.zeros((n_emb, 16), device=DEV)
-    ops.shader_prep_bwd(T(g), T(idx), 1 / 128.0, n_emb, d_scene, d_app)
+    ops.shader_prep_bwd(T(g), T(bounds), T(ray_idx), 1 / 128.0, d_scene, d_app)
     gf = g.astype(np.float32)[:, :16] / 128.0
     np.testing.assert_allclose(N(d_scene)[:, 1:], gf[:, 1:], rtol=1e-6)
     assert (N(d_scene)[:, 0] == 7.0).all()                       # the density-logit column is not touched
     ref = np.zeros((n_emb, 16), np.float64)
-    np.add.at(ref, idx, gf.astype(np.float64))
+    np.add.at(ref, np.repeat(ray_idx, lens), gf.astype(np.float64))
     assert_close(N(d_app), ref, rtol=1e-4, atol_frac=1e-5, name="d_app_emb")
+    d2 = torch.zeros((n, 16), device=DEV)
+    ops.shader_prep_bwd(T(g), T(bounds), None, 1 / 128.0, d2, None)   # no embedding: only the feature gradient
+    np.testing.assert_allclose(N(d2)[:, 1:], gf[:, 1:], rtol=1e-6)
 
 
 # -------------------------------------------------------------------------------- composite ----
