@@ -37,42 +37,85 @@ hash_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_p
   for (int q = 0; q < 4; q++) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 }
 
-// Backward: thread per (sample, level); 8 vector reductions red.global.add.v2.f32 into the fp32
-// gradient table (the reference accumulates fp16 atomics of grad*128 and divides later; fp32 is
-// both faster on B200's L2 atomic units and more accurate).  Zero-gradient rows are skipped like
-// the reference (Hash3DAnchored.cu:149).
+// Backward: a warp owns 32 CONSECUTIVE samples at one level (samples of a ray are consecutive, so at the
+// coarse levels many lanes fall into the same grid cell and hit the same 8 table entries).  Lanes are grouped
+// into runs of identical (cell, volume); when the warp has few runs, the 16 per-run sums (8 corners x 2
+// channels) are formed with a segmented shuffle scan and only the run's last lane issues the 8 vector
+// reductions red.global.add.v2.f32 — up to 32x fewer L2 atomics at the coarse levels; fine levels (every
+// lane its own run) take the direct path.  fp32 accumulation (the reference accumulates fp16 atomics of
+// grad*128, Hash3DAnchored.cu:145-151, and casts/divides afterwards); zero-gradient rows are skipped (:149).
 template <bool GRAD_F16>
 __global__ void __launch_bounds__(256)
 hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bias_pool, int n_volumes,
                 int local_size, const float* __restrict__ pts, const int* __restrict__ vol,
                 int vol_stride, int n_pts, const void* __restrict__ grad_feat, float grad_mul,
                 float* __restrict__ grad_table) {
-  const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int l = int(gid & 15);
-  const int64_t i = gid >> 4;
-  if (i >= n_pts) return;
-  float g0, g1;
-  if (GRAD_F16) {
-    const __half2 g = reinterpret_cast<const __half2*>(grad_feat)[i * 16 + l];
-    const float2 gf = __half22float2(g);
-    g0 = gf.x; g1 = gf.y;
-  } else {
-    const float2 gf = reinterpret_cast<const float2*>(grad_feat)[i * 16 + l];
-    g0 = gf.x; g1 = gf.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int l = int(warp_id & 15);
+  const int64_t i = (warp_id >> 4) * 32 + lane;
+  const bool valid = i < n_pts;
+  float g0 = 0.f, g1 = 0.f;
+  if (valid) {
+    if (GRAD_F16) {
+      const float2 gf = __half22float2(reinterpret_cast<const __half2*>(grad_feat)[i * 16 + l]);
+      g0 = gf.x; g1 = gf.y;
+    } else {
+      const float2 gf = reinterpret_cast<const float2*>(grad_feat)[i * 16 + l];
+      g0 = gf.x; g1 = gf.y;
+    }
   }
-  if (g0 == 0.f && g1 == 0.f) return;
+  const bool live = valid && !(g0 == 0.f && g1 == 0.f);
+  if (!__any_sync(0xffffffffu, live)) return;
   g0 *= grad_mul; g1 *= grad_mul;
-  const float p0 = __ldg(pts + i * 3), p1 = __ldg(pts + i * 3 + 1), p2 = __ldg(pts + i * 3 + 2);
-  const float x0 = fmul(fadd(p0, 1.f), .5f), x1 = fmul(fadd(p1, 1.f), .5f), x2 = fmul(fadd(p2, 1.f), .5f);
-  const int v = __ldg(vol + i * vol_stride);
-  const int tv = l * n_volumes + v;
   Corner8 c;
-  corners(x0, x1, x2, level_scale(l), prim_pool + tv * 3, bias_pool + tv * 3, (unsigned)local_size, c);
-  float* base = grad_table + size_t(l) * local_size;
+  int v = -1;
+  if (live) {
+    const float p0 = __ldg(pts + i * 3), p1 = __ldg(pts + i * 3 + 1), p2 = __ldg(pts + i * 3 + 2);
+    const float x0 = fmul(fadd(p0, 1.f), .5f), x1 = fmul(fadd(p1, 1.f), .5f), x2 = fmul(fadd(p2, 1.f), .5f);
+    v = __ldg(vol + i * vol_stride);
+    const int tv = l * n_volumes + v;
+    corners(x0, x1, x2, level_scale(l), prim_pool + tv * 3, bias_pool + tv * 3, (unsigned)local_size, c);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    float2* dst = reinterpret_cast<float2*>(base + size_t(c.idx[k]) * 2);
-    atomicAdd(dst, make_float2(c.w[k] * g0, c.w[k] * g1));
+    for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
+    c.cell[0] = c.cell[1] = c.cell[2] = 0;
+  }
+  // run heads: key differs from the previous lane (dead lanes never merge)
+  const unsigned pcx = __shfl_up_sync(0xffffffffu, c.cell[0], 1), pcy = __shfl_up_sync(0xffffffffu, c.cell[1], 1),
+                 pcz = __shfl_up_sync(0xffffffffu, c.cell[2], 1);
+  const int prev_v = __shfl_up_sync(0xffffffffu, v, 1);       // dead lanes carry v = -1 and never merge
+  const bool head = (lane == 0) || !live || c.cell[0] != pcx || c.cell[1] != pcy || c.cell[2] != pcz || v != prev_v;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  float* base = grad_table + size_t(l) * local_size;
+  if (__popc(heads) > 20) {                                   // mostly singleton runs: direct reductions
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        atomicAdd(reinterpret_cast<float2*>(base + size_t(c.idx[k]) * 2), make_float2(c.w[k] * g0, c.w[k] * g1));
+    }
+    return;
+  }
+  // segmented inclusive scan within runs; the last lane of each run holds the run total
+  const unsigned below = heads & ((2u << lane) - 1u);         // heads at or below my lane
+  const int run_start = 31 - __clz(below);
+  float s[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { s[2 * k] = c.w[k] * g0; s[2 * k + 1] = c.w[k] * g1; }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool take = (lane - o) >= run_start;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const float u = __shfl_up_sync(0xffffffffu, s[k], o);
+      if (take) s[k] += u;
+    }
+  }
+  const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+  if (live && tail) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      atomicAdd(reinterpret_cast<float2*>(base + size_t(c.idx[k]) * 2), make_float2(s[2 * k], s[2 * k + 1]));
   }
 }
 
@@ -113,7 +156,7 @@ extern "C" int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_
                             void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(prim_pool && bias_pool && pts && vol && grad_feat && grad_table, "f2b_hash_bwd: null pointer");
-  const int blocks = div_up(int64_t(n_pts) * 16, 256);
+  const int blocks = div_up(int64_t(div_up(n_pts, 32)) * 16 * 32, 256);    // one warp per (32 samples, level)
   if (grad_is_f16)
     hash_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts,
                                                                  vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table);

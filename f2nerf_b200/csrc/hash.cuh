@@ -13,6 +13,7 @@ __device__ __forceinline__ float level_scale(int l) {
 struct Corner8 {
   unsigned idx[8];   // order 000,001,010,011,100,101,110,111 (z fastest)
   float w[8];
+  unsigned cell[3];  // integer cell coordinates (exact run key for the backward's merging)
 };
 
 // index/weight computation shared by forward and backward (Hash3DAnchored.cu:27-66)
@@ -23,6 +24,7 @@ __device__ __forceinline__ void corners(float x0, float x1, float x2, float scal
               pz = ffma(x2, scale, __ldg(bias + 2));
   const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
   const unsigned ix = (unsigned)fx, iy = (unsigned)fy, iz = (unsigned)fz;   // cvt.rzi.u32.f32 (saturating)
+  c.cell[0] = ix; c.cell[1] = iy; c.cell[2] = iz;
   const unsigned pa = (unsigned)__ldg(prim), pb = (unsigned)__ldg(prim + 1), pc = (unsigned)__ldg(prim + 2);
   const unsigned hx0 = ix * pa, hx1 = hx0 + pa, hy0 = iy * pb, hy1 = hy0 + pb, hz0 = iz * pc, hz1 = hz0 + pc;
   const bool pow2 = (local_size & (local_size - 1)) == 0;

@@ -140,15 +140,15 @@ __device__ __forceinline__ void load_slice(const TransInfo* __restrict__ T, int 
   s.c[0] = cd.x; s.c[1] = cd.y; s.c[2] = cd.z; s.dis = cd.w;
 }
 
-// sum of the 4 lane partials in the reference's tree order: (g0+g1) + (g2+g3).  Only the 4 lanes
-// of the ray take part (rays of one warp leave the march loop at different times).
-__device__ __forceinline__ float group_sum(float g, unsigned gmask) {
-  g = fadd(g, __shfl_xor_sync(gmask, g, 1));
-  g = fadd(g, __shfl_xor_sync(gmask, g, 2));
+// sum of the 4 lane partials in the reference's tree order: (g0+g1) + (g2+g3).  xor 1 / xor 2 stay inside
+// the ray's 4-lane group; the whole warp executes them together (constant full mask).
+__device__ __forceinline__ float group_sum(float g) {
+  g = fadd(g, __shfl_xor_sync(0xffffffffu, g, 1));
+  g = fadd(g, __shfl_xor_sync(0xffffffffu, g, 2));
   return g;
 }
 
-template <bool FILL>
+template <int MODE>   // 0: count only, 1: fill at pts_idx_bounds, 2: one pass into per-ray scratch slots of 1024 samples
 __global__ void __launch_bounds__(kRaysPerBlock* kLanesPerRay)
 march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ trans,
              const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -174,19 +174,22 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
 
   Dfs dfs;
   dfs.stack = s_stack + lane * kStackPitch;
-  const unsigned gmask = 0xFu << (lane & ~(kLanesPerRay - 1));
   dfs.sp = 0; dfs.n_hits = 0; dfs.max_hits = max_hits;
   dfs.st = (int(d[0] > 0.f) << 2) | (int(d[1] > 0.f) << 1) | int(d[2] > 0.f);
   dfs.stack[0] = 0;                                    // root, cursor -1
 
+  constexpr bool FILL = MODE != 0;
   int cap = F2B_MAX_SAMPLE_PER_RAY;
-  int out_base = 0;
-  if (FILL) {
+  size_t out_base = 0;
+  if (MODE == 1) {
     out_base = bounds[ray * 2];
-    cap = bounds[ray * 2 + 1] - out_base;
+    cap = bounds[ray * 2 + 1] - int(out_base);
+  } else if (MODE == 2) {
+    out_base = size_t(ray) * F2B_MAX_SAMPLE_PER_RAY;
   }
 
   Hit hit;
+  hit.node = 0; hit.trans_idx = 0; hit.near = 0.f; hit.far = 0.f;
   bool have = next_hit(dfs, nodes, o, d, near0, far0, hit);
   if (FILL && active && sub == 0) first_oct_dis[ray] = have ? hit.near : 1e9f;
 
@@ -195,15 +198,15 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
     float t = hit.near, far = hit.far;
     int cur_node = hit.node, cur_trans = hit.trans_idx, loaded_trans = -1;
     bool first = true;
-    TransSlice ts;
+    TransSlice ts = {};
     float rclip = 1.f;
-    // Warp-uniform trip count: every lane stays in the loop until the slowest ray of the warp is done and
-    // the warp re-converges at the __any_sync each step, so the 8 ray-groups execute the step together
-    // (a data-dependent `while (k < cap && have)` lets the groups drift apart and serialises them 8x).
+    // Warp-uniform loop: every lane executes every step's arithmetic and its full-mask shuffles until the
+    // slowest ray of the warp is done (finished rays compute on stale values, all side effects are
+    // predicated on `running`).  Partial-mask shuffles inside a data-dependent loop cost a
+    // WARPSYNC.COLLECTIVE each (~30 per step); with a constant full mask they are plain SHFL.BFLY.
     bool running = have && cap > 0;
     while (__any_sync(0xffffffffu, running)) {
-      if (running) {
-      if (cur_trans != loaded_trans) {
+      if (running && cur_trans != loaded_trans) {
         load_slice(trans + cur_trans, sub, ts);
         loaded_trans = cur_trans;
         // cur_radius = |o - center| / dis_summary, clipped at 1   (PersSampler.cu:262-263)
@@ -228,58 +231,60 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
       float proj[3];
 #pragma unroll
       for (int r = 0; r < 3; r++) {
-        const float j0 = group_sum(ffma(ts.w[r][0], T0[0], ffma(ts.w[r][1], T0[1], fmul(ts.w[r][2], T0[2]))), gmask);
-        const float j1 = group_sum(ffma(ts.w[r][0], T1[0], ffma(ts.w[r][1], T1[1], fmul(ts.w[r][2], T1[2]))), gmask);
-        const float j2 = group_sum(ffma(ts.w[r][0], T2[0], ffma(ts.w[r][1], T2[1], fmul(ts.w[r][2], T2[2]))), gmask);
+        const float j0 = group_sum(ffma(ts.w[r][0], T0[0], ffma(ts.w[r][1], T0[1], fmul(ts.w[r][2], T0[2]))));
+        const float j1 = group_sum(ffma(ts.w[r][0], T1[0], ffma(ts.w[r][1], T1[1], fmul(ts.w[r][2], T1[2]))));
+        const float j2 = group_sum(ffma(ts.w[r][0], T2[0], ffma(ts.w[r][1], T2[1], fmul(ts.w[r][2], T2[2]))));
         proj[r] = ffma(j0, d[0], ffma(j1, d[1], fmul(j2, d[2])));
+      }
+      float w[3] = {0.f, 0.f, 0.f};
+      if (FILL) {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          w[r] = group_sum(ffma(ts.w[r][0], V[0], ffma(ts.w[r][1], V[1], fmul(ts.w[r][2], V[2]))));
       }
       const float den = fadd(fsqrt(ffma(proj[0], proj[0], ffma(proj[1], proj[1], fmul(proj[2], proj[2])))), 1e-6f);
       float step = fdiv(fmul(sample_l, __ldg(noise + k)), den);
       if (scale_by_dis) step = fmul(rclip, step);
 
-      if (!first) {
-        if (FILL) {
-          float w[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-            w[r] = group_sum(ffma(ts.w[r][0], V[0], ffma(ts.w[r][1], V[1], fmul(ts.w[r][2], V[2]))), gmask);
-          if (active) {
-            const size_t idx = size_t(out_base) + k;
+      if (running) {
+        if (!first) {
+          if (FILL && active) {
+            const size_t idx = out_base + k;
             if (sub == 0) {
               o_pts[idx * 3] = w[0]; o_pts[idx * 3 + 1] = w[1]; o_pts[idx * 3 + 2] = w[2];
             } else if (sub == 1) {
-              o_dirs[idx * 3] = d[0]; o_dirs[idx * 3 + 1] = d[1]; o_dirs[idx * 3 + 2] = d[2];
+              if (MODE == 1) { o_dirs[idx * 3] = d[0]; o_dirs[idx * 3 + 1] = d[1]; o_dirs[idx * 3 + 2] = d[2]; }
             } else if (sub == 2) {
               o_dt[idx] = fmul(step, den);
               o_t[idx] = t;
             } else {
-              o_anchors[idx * 3] = cur_trans; o_anchors[idx * 3 + 1] = cur_node; o_anchors[idx * 3 + 2] = 0;
+              if (MODE == 1) { o_anchors[idx * 3] = cur_trans; o_anchors[idx * 3 + 1] = cur_node; o_anchors[idx * 3 + 2] = 0; }
+              else { o_anchors[idx * 2] = cur_trans; o_anchors[idx * 2 + 1] = cur_node; }
             }
           }
+          k++;
         }
-        k++;
-      }
-      // advance; hop leaves with an integer multiple of the step (PersSampler.cu:291-303; the
-      // reference build contracts cur_t + step*float(n) into one fma)
-      float tn = fadd(t, step);
-      if (tn > far) {
-        for (;;) {
-          have = next_hit(dfs, nodes, o, d, near0, far0, hit);
-          if (!have) break;
-          far = hit.far; cur_node = hit.node; cur_trans = hit.trans_idx;
-          const float nf = ceilf(fmaxf(fdiv(fsub(hit.near, t), step), 1.f));
-          const int n = (int)nf;                       // cvt.rzi.s32.f32 (saturating)
-          tn = ffma(step, (float)n, t);
-          if (!(tn > far)) break;
+        // advance; hop leaves with an integer multiple of the step (PersSampler.cu:291-303; the
+        // reference build contracts cur_t + step*float(n) into one fma)
+        float tn = fadd(t, step);
+        if (tn > far) {
+          for (;;) {
+            have = next_hit(dfs, nodes, o, d, near0, far0, hit);
+            if (!have) break;
+            far = hit.far; cur_node = hit.node; cur_trans = hit.trans_idx;
+            const float nf = ceilf(fmaxf(fdiv(fsub(hit.near, t), step), 1.f));
+            const int n = (int)nf;                       // cvt.rzi.s32.f32 (saturating)
+            tn = ffma(step, (float)n, t);
+            if (!(tn > far)) break;
+          }
         }
-      }
-      t = tn;
-      first = false;
-      running = (k < cap) && have;
+        t = tn;
+        first = false;
+        running = (k < cap) && have;
       }
     }
   }
-  if (!FILL) {
+  if (MODE != 1) {
     if (count_all_hits) {                                      // exact n_all_oct_intersect (:353,378), informational EMA only
       while (next_hit(dfs, nodes, o, d, near0, far0, hit)) {}
     }
@@ -288,6 +293,29 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
       if (dfs.n_hits) atomicAdd(total_hits, dfs.n_hits);
     }
   }
+}
+
+// Second half of the one-pass sampler: copy each ray's samples from its scratch slot to the compact,
+// ray-ordered outputs (the reference's cumsum layout), regenerating dirs / anchors[:,2]; warp per ray.
+__global__ void __launch_bounds__(256)
+sampler_gather_kernel(const float* __restrict__ rays_d, const int* __restrict__ bounds, int n_rays,
+                      const float* __restrict__ s_pts, const float* __restrict__ s_dt, const float* __restrict__ s_t,
+                      const int* __restrict__ s_anchors, float* __restrict__ pts, float* __restrict__ dirs,
+                      float* __restrict__ dt, float* __restrict__ t, int* __restrict__ anchors) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= n_rays) return;
+  const int beg = bounds[2 * ray], n = bounds[2 * ray + 1] - beg;
+  const size_t src = size_t(ray) * F2B_MAX_SAMPLE_PER_RAY;
+  const float d0 = rays_d[ray * 3], d1 = rays_d[ray * 3 + 1], d2 = rays_d[ray * 3 + 2];
+  for (int i = lane; i < 3 * n; i += 32) {              // 12-byte rows as flat float streams: fully coalesced
+    pts[size_t(beg) * 3 + i] = s_pts[src * 3 + i];
+    const int c = i % 3;
+    dirs[size_t(beg) * 3 + i] = c == 0 ? d0 : (c == 1 ? d1 : d2);
+    const int j = i / 3;
+    anchors[size_t(beg) * 3 + i] = c == 2 ? 0 : s_anchors[(src + j) * 2 + c];
+  }
+  for (int i = lane; i < n; i += 32) { dt[beg + i] = s_dt[src + i]; t[beg + i] = s_t[src + i]; }
 }
 
 // ---- edge samples (PersSampler.cu:436-452) ----------------------------------------------------
@@ -428,7 +456,7 @@ extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void
   if (n_rays == 0) return check_launch("f2b_sampler_count");      // empty batch: totals = {0, 0}
   F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && ray_counts && pts_idx_bounds,
               "f2b_sampler_count: null pointer");
-  march_kernel<false><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
+  march_kernel<0><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
       far, sample_l, scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, nullptr,
       nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -445,11 +473,42 @@ extern "C" int f2b_sampler_fill(const void* tree_nodes, int n_nodes, const void*
   F2B_REQUIRE(n_rays >= 0 && n_nodes > 0, "f2b_sampler_fill: bad sizes");
   if (n_rays == 0) return F2B_OK;
   F2B_REQUIRE(tree_nodes && trans && pts_idx_bounds && first_oct_dis, "f2b_sampler_fill: null pointer");
-  march_kernel<true><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, as_stream(stream)>>>(
+  march_kernel<1><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, as_stream(stream)>>>(
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
       far, sample_l, scale_by_dis, max_oct_intersect_per_ray, 0, nullptr, nullptr, pts_idx_bounds, pts,
       dirs, dt, t, anchors, first_oct_dis);
   return check_launch("f2b_sampler_fill");
+}
+
+extern "C" int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                                 const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                                 float near, float far, float sample_l, int scale_by_dis,
+                                 int max_oct_intersect_per_ray, int count_all_hits, float* s_pts, float* s_dt,
+                                 float* s_t, int* s_anchors, int* ray_counts, int* pts_idx_bounds, int* totals,
+                                 float* first_oct_dis, void* stream) {
+  F2B_REQUIRE(n_rays >= 0 && n_nodes > 0 && n_trans >= 0, "f2b_sampler_march: bad sizes");
+  F2B_REQUIRE(totals, "f2b_sampler_march: null totals");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(totals, 0, 2 * sizeof(int), st);
+  if (n_rays == 0) return check_launch("f2b_sampler_march");
+  F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && s_pts && s_dt && s_t && s_anchors && ray_counts &&
+              pts_idx_bounds && first_oct_dis, "f2b_sampler_march: null pointer");
+  march_kernel<2><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
+      (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l,
+      scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, s_pts, nullptr, s_dt, s_t,
+      s_anchors, first_oct_dis);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(ray_counts, n_rays, pts_idx_bounds, totals);
+  return check_launch("f2b_sampler_march");
+}
+
+extern "C" int f2b_sampler_gather(const float* rays_d, const int* pts_idx_bounds, int n_rays, const float* s_pts,
+                                  const float* s_dt, const float* s_t, const int* s_anchors, float* pts, float* dirs,
+                                  float* dt, float* t, int* anchors, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(rays_d && pts_idx_bounds && s_pts && s_dt && s_t && s_anchors, "f2b_sampler_gather: null pointer");
+  sampler_gather_kernel<<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(
+      rays_d, pts_idx_bounds, n_rays, s_pts, s_dt, s_t, s_anchors, pts, dirs, dt, t, anchors);
+  return check_launch("f2b_sampler_gather");
 }
 
 extern "C" int f2b_edge_samples(const void* edge_pool, const void* trans, const int* edge_idx,

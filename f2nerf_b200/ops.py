@@ -53,6 +53,30 @@ def sampler_fill(tree_nodes, trans, rays_o, rays_d, noise, near, far, sample_l, 
     return pts, dirs, dt, t, anchors, first
 
 
+def sampler_march(tree_nodes, trans, rays_o, rays_d, noise, near, far, sample_l, scale_by_dis, max_hits, scratch,
+                  count_all_hits=False):
+    """One-pass march into per-ray scratch slots -> (bounds, totals, first_oct_dis).  scratch = (s_pts, s_dt, s_t, s_anchors)."""
+    R = rays_o.shape[0]
+    counts = dev_empty((max(R, 1),), I32, rays_o)
+    bounds = dev_empty((R, 2), I32, rays_o)
+    totals = dev_empty((2,), I32, rays_o)
+    first = dev_empty((R, 1), F32, rays_o)
+    call("f2b_sampler_march", tree_nodes, tree_nodes.numel() // 64, trans, trans.numel() // 544, rays_o, rays_d, noise, R,
+         float(near), float(far), float(sample_l), int(bool(scale_by_dis)), int(max_hits), int(bool(count_all_hits)),
+         *scratch, counts, bounds, totals, first, stream())
+    return bounds, totals, first
+
+
+def sampler_gather(rays_d, bounds, n_pts, scratch):
+    pts = dev_empty((n_pts, 3), F32, rays_d)
+    dirs = dev_empty((n_pts, 3), F32, rays_d)
+    dt = dev_empty((n_pts,), F32, rays_d)
+    t = dev_empty((n_pts,), F32, rays_d)
+    anchors = dev_empty((n_pts, 3), I32, rays_d)
+    call("f2b_sampler_gather", rays_d, bounds, bounds.shape[0], *scratch, pts, dirs, dt, t, anchors, stream())
+    return pts, dirs, dt, t, anchors
+
+
 def edge_samples(edge_pool, trans, edge_idx, edge_coord):
     n = edge_idx.shape[0]
     out_pts = dev_empty((n, 2, 3), F32, edge_coord)

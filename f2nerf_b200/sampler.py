@@ -98,12 +98,22 @@ class PersSampler:
             rays_noise = self.make_noise(n_rays, rays_o.device)
         args = (self.tree_nodes_gpu_, self.pers_trans_gpu_, rays_o, rays_d, rays_noise, self.global_near_, 1e8,
                 self.sample_l_, self.scale_by_dis_, self.max_oct_intersect_per_ray_)
-        bounds, totals = ops.sampler_count(*args, count_all_hits=self.exact_oct_stat_)
+        scratch = self._scratch(n_rays, rays_o.device)
+        bounds, totals, first = ops.sampler_march(*args, scratch, count_all_hits=self.exact_oct_stat_)
         n_all_pts, n_all_oct = (int(v) for v in totals.tolist())            # the one sync
         if gdp.mode_ != VALIDATE and n_rays > 0:
             gdp.sampled_oct_per_ray_ = gdp.sampled_oct_per_ray_ * .9 + (n_all_oct / n_rays) * .1
-        pts, dirs, dt, t, anchors, first = ops.sampler_fill(*args, bounds, n_all_pts)
+        pts, dirs, dt, t, anchors = ops.sampler_gather(rays_d, bounds, n_all_pts, scratch)
         return SampleResultFlex(pts, dirs, dt, t, anchors, bounds, first)
+
+    def _scratch(self, n_rays, dev):
+        """Persistent one-pass march scratch: a 1024-sample slot per ray (28 B/sample), grown on demand."""
+        cap = max(n_rays, 1) * MAX_SAMPLE_PER_RAY
+        if getattr(self, "_scratch_cap", 0) < cap or self._scratch_bufs[0].device != dev:
+            f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+            self._scratch_bufs = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
+            self._scratch_cap = cap
+        return self._scratch_bufs
 
     def GetEdgeSamples(self, n_pts):
         """PersSampler::GetEdgeSamples (PersSampler.cu:454-473): (out_pts [n,2,3], out_idx [n,2])."""

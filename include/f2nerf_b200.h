@@ -65,6 +65,21 @@ int f2b_sampler_fill(const void* tree_nodes, int n_nodes, const void* trans, int
                      float* pts /* [P,3] warped */, float* dirs /* [P,3] */, float* dt /* [P] */,
                      float* t /* [P] */, int* anchors /* [P,3] */, float* first_oct_dis /* [n_rays] */,
                      void* stream);
+/* One-pass variant (what the host mirrors use): the march runs ONCE, each ray writing into its own scratch slot
+ * of F2B_MAX_SAMPLE_PER_RAY samples (caller-owned scratch: s_pts [R*1024,3] f32, s_dt/s_t [R*1024] f32,
+ * s_anchors [R*1024,2] i32 = trans_idx,node), then f2b_sampler_gather packs the slots into the reference's
+ * compact ray-ordered layout (a 28 B/sample copy instead of a second traverse-and-march).  Outputs are
+ * bit-identical to f2b_sampler_count + f2b_sampler_fill. */
+int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                      const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                      float near, float far, float sample_l, int scale_by_dis,
+                      int max_oct_intersect_per_ray, int count_all_hits,
+                      float* s_pts, float* s_dt, float* s_t, int* s_anchors,
+                      int* ray_counts /* [n_rays] */, int* pts_idx_bounds /* [n_rays,2] out */, int* totals /* [2] out */,
+                      float* first_oct_dis /* [n_rays] out */, void* stream);
+int f2b_sampler_gather(const float* rays_d, const int* pts_idx_bounds, int n_rays,
+                       const float* s_pts, const float* s_dt, const float* s_t, const int* s_anchors,
+                       float* pts, float* dirs, float* dt, float* t, int* anchors, void* stream);
 /* GetEdgeSamplesKernel (PersSampler.cu:436-452). */
 int f2b_edge_samples(const void* edge_pool, const void* trans, const int* edge_idx,
                      const float* edge_coord /* [n,2] */, int n_pts,

@@ -18,7 +18,7 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_RAYS = 48
+N_RAYS = 12
 
 
 def main():

@@ -101,7 +101,7 @@ def hash_bwd(prim, bias, n_volumes, local_size, scales, pts, vol, vol_stride, gr
     g = np.zeros(pool_size * 2, np.float64)
     lib().orc_hash_bwd(_p(c(prim, np.int32)), _p(c(bias, np.float32)), I(n_volumes), I(local_size),
                        _p(c(scales, np.float32)), _p(c(pts, np.float32)), _p(c(vol, np.int32)), I(vol_stride),
-                       I(pts.shape[0]), _p(c(grad_feat, np.float32)), F(grad_mul), I(int(half_products)), _p(g))
+                       I(pts.shape[0]), _p(c(grad_feat, np.float32)), F(grad_mul), I(int(half_products)), _p(g))   # half_products: 0 exact, 1 fp16 products, 2 fp16 products + fp16 accumulation
     return g.reshape(pool_size, 2)
 
 

@@ -104,5 +104,8 @@ def render_train(sc, rays_o, rays_dn, noise, bg, field, shader_params, app_emb=N
     out["grad_feat_pool_half_products"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
                                                      np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32),
                                                      1.0 / LOSS_SCALE, field["table16"].shape[0], half_products=True)
+    out["grad_feat_pool_half_accum"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
+                                                  np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32),
+                                                  1.0 / LOSS_SCALE, field["table16"].shape[0], half_products=2)
     out["d_scene"] = d_scene
     return out

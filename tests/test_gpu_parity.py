@@ -72,6 +72,21 @@ def test_sampler_bit_exact(scene, oracle, n_rays, scale_by_dis, noise_kind, samp
     np.testing.assert_array_equal(got["anchors"], ref["anchors"])
 
 
+def test_sampler_one_pass_equals_two_pass(scene, oracle):
+    """f2b_sampler_march + f2b_sampler_gather (one march into scratch slots) == count + fill, bit for bit."""
+    from f2nerf_b200 import GlobalDataPool, PersSampler, TRAIN
+    o, d, dn, _ = make_rays(scene, 777, seed=3)
+    noise = (np.random.default_rng(8).random(1024 + 777 + 10, dtype=np.float32) + .5).astype(np.float32)
+    two = run_sampler_gpu(scene, o, dn, noise, 0.05, 1 / 256, True)
+    gdp = GlobalDataPool(); gdp.mode_ = TRAIN
+    ps = PersSampler(gdp, scene["nodes"], scene["trans"], scene["edges"], near=0.05, sample_l=1 / 256, scale_by_dis=True)
+    s = ps.GetSamples(T(o), T(d), None, rays_noise=T(noise))
+    np.testing.assert_array_equal(N(s.pts_idx_bounds), two["bounds"])
+    np.testing.assert_array_equal(N(s.anchors), two["anchors"])
+    for k, v in (("pts", s.pts), ("dirs", s.dirs), ("dt", s.dt), ("t", s.t), ("first_oct_dis", s.first_oct_dis)):
+        np.testing.assert_array_equal(N(v).view(np.uint32), two[k].view(np.uint32), err_msg=k)
+
+
 def test_sampler_edge_cases(scene, oracle):
     from f2nerf_b200 import ops
     # rays that miss everything (start far outside, pointing away) and an empty batch

@@ -168,10 +168,12 @@ def test_render_train_vs_reference(ref):
     gref = ref["grad_feat_pool"]
     summary["feat_pool_oracle_exact_vs_ref"] = cosd(orc["grad_feat_pool"], gref)
     summary["feat_pool_oracle_halfprod_vs_ref"] = cosd(orc["grad_feat_pool_half_products"], gref)
+    summary["feat_pool_oracle_halfaccum_vs_ref"] = cosd(orc["grad_feat_pool_half_accum"], gref)
     summary["feat_pool_ours_vs_oracle_exact"] = cosd(N(field.feat_pool_.grad), orc["grad_feat_pool"])
     json.dump(summary, open(os.path.join(ROOT, "gpurun_out", "ref_grad_parity.json"), "w"), indent=1)
     for name in ("field_mlp", "shader_mlp", "app_emb"):
         assert summary[name]["cos"] >= 0.98 and summary[name]["rel_l2"] <= 0.2, (name, summary[name])
     assert summary["feat_pool_ours_vs_oracle_exact"] >= 0.995, summary
-    assert summary["feat_pool_oracle_halfprod_vs_ref"] > summary["feat_pool_oracle_exact_vs_ref"], summary
-    assert summary["feat_pool_oracle_halfprod_vs_ref"] >= 0.95 or summary["feat_pool"]["cos"] >= 0.98, summary
+    # ours == the exact sum; the reference's fp16 accumulation (emulated, in sample order) is what moves it away
+    assert summary["feat_pool_oracle_halfaccum_vs_ref"] > summary["feat_pool_oracle_exact_vs_ref"] + 0.05 or \
+        summary["feat_pool"]["cos"] >= 0.98, summary
