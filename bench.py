@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h),
                                   nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
-                time.sleep(0.05)
+                time.sleep(0.1)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)[:120]
 
@@ -161,13 +161,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) ------------------------------------------------------
+    # ---- device-resident timing (value): K steps bracketed by barrier + synchronize, CUDA events --------
     for _ in range(args.warmup):
         train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
     clocks = ClockSampler(local)
     clocks.start()
     barrier()
-    _lib.TRACE = []
     launches0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -179,8 +178,13 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    trace, _lib.TRACE = _lib.TRACE, None
     launches = _lib.LAUNCHES - launches0
+    # ---- per-kernel CUDA-event trace over the same steps (separate loop: event pairs around every C-ABI call) --
+    _lib.TRACE = []
+    for _ in range(args.steps):
+        train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
+    barrier()
+    trace, _lib.TRACE = _lib.TRACE, None
     # ---- end-to-end timing: pinned host rays -> device, loss -> host, every step ----------------
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -36,8 +36,7 @@ def main():
             "train_noise", "train_bg", "train_edge_idx", "train_edge_coord", "train_pts", "train_dt", "train_t", "train_anchors",
             "train_bounds", "train_colors", "train_disparity", "train_depth", "train_weights", "train_idx_start_end",
             "train_first_oct_dis", "train_tree_nodes_after", "train_weight_stats_after", "train_alpha_stats_after",
-            "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb",
-            "grad_feat_pool_nz_idx", "grad_feat_pool_nz_val"]
+            "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb"]
     data = {k: np.load(os.path.join(out, k + ".npy")) for k in keep}
     # the level scales as the device computes them (MUFU.EX2): the oracle takes them as an input
     sys.path.insert(0, ROOT)

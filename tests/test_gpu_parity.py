@@ -74,16 +74,21 @@ def test_sampler_bit_exact(scene, oracle, n_rays, scale_by_dis, noise_kind, samp
 
 def test_sampler_one_pass_equals_two_pass(scene, oracle):
     """f2b_sampler_march + f2b_sampler_gather (one march into scratch slots) == count + fill, bit for bit."""
-    from f2nerf_b200 import GlobalDataPool, PersSampler, TRAIN
-    o, d, dn, _ = make_rays(scene, 777, seed=3)
-    noise = (np.random.default_rng(8).random(1024 + 777 + 10, dtype=np.float32) + .5).astype(np.float32)
+    from f2nerf_b200 import ops
+    n = 777
+    o, d, dn, _ = make_rays(scene, n, seed=3)
+    noise = (np.random.default_rng(8).random(1024 + n + 10, dtype=np.float32) + .5).astype(np.float32)
     two = run_sampler_gpu(scene, o, dn, noise, 0.05, 1 / 256, True)
-    gdp = GlobalDataPool(); gdp.mode_ = TRAIN
-    ps = PersSampler(gdp, scene["nodes"], scene["trans"], scene["edges"], near=0.05, sample_l=1 / 256, scale_by_dis=True)
-    s = ps.GetSamples(T(o), T(d), None, rays_noise=T(noise))
-    np.testing.assert_array_equal(N(s.pts_idx_bounds), two["bounds"])
-    np.testing.assert_array_equal(N(s.anchors), two["anchors"])
-    for k, v in (("pts", s.pts), ("dirs", s.dirs), ("dt", s.dt), ("t", s.t), ("first_oct_dis", s.first_oct_dis)):
+    args = (T(scene["nodes"]), T(scene["trans"]), T(o), T(dn), T(noise), 0.05, 1e8, 1 / 256, True, 1024)
+    cap = n * 1024
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=DEV)
+    scratch = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=DEV))
+    bounds, totals, first = ops.sampler_march(*args, scratch, count_all_hits=True)
+    assert totals.tolist() == [two["pts"].shape[0], two["n_hits"]]
+    pts, dirs, dt, t, anchors = ops.sampler_gather(T(dn), bounds, int(totals[0]), scratch)
+    np.testing.assert_array_equal(N(bounds), two["bounds"])
+    np.testing.assert_array_equal(N(anchors), two["anchors"])
+    for k, v in (("pts", pts), ("dirs", dirs), ("dt", dt), ("t", t), ("first_oct_dis", first)):
         np.testing.assert_array_equal(N(v).view(np.uint32), two[k].view(np.uint32), err_msg=k)
 
 
