@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(256)
 compact_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ old_bounds,
                const int* __restrict__ new_bounds, int n_rays, const float* __restrict__ pts,
                const float* __restrict__ dirs, const float* __restrict__ dt, const float* __restrict__ t,
-               const int* __restrict__ anchors, float* __restrict__ pts_o, float* __restrict__ dirs_o,
-               float* __restrict__ dt_o, float* __restrict__ t_o, int* __restrict__ anchors_o) {
+               const int* __restrict__ anchors, const uint4* __restrict__ feat, float* __restrict__ pts_o,
+               float* __restrict__ dirs_o, float* __restrict__ dt_o, float* __restrict__ t_o,
+               int* __restrict__ anchors_o, uint4* __restrict__ feat_o) {
   const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ray >= n_rays) return;
@@ -102,6 +103,10 @@ compact_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ old_bou
       }
       dt_o[o] = dt[s];
       t_o[o] = t[s];
+      if (feat) {                                  // the sample's 32 encoded halfs (64 B) from the early-stop pass
+#pragma unroll
+        for (int c = 0; c < 4; c++) feat_o[o * 4 + c] = feat[s * 4 + c];
+      }
     }
     out += __popc(m);
   }
@@ -340,11 +345,13 @@ extern "C" int f2b_early_stop(const float* logit, int logit_stride, const float*
 
 extern "C" int f2b_compact_samples(const uint8_t* keep, const int* old_bounds, const int* new_bounds, int n_rays,
                                    const float* pts, const float* dirs, const float* dt, const float* t,
-                                   const int* anchors, float* pts_o, float* dirs_o, float* dt_o, float* t_o,
-                                   int* anchors_o, void* stream) {
+                                   const int* anchors, const void* feat_f16, float* pts_o, float* dirs_o,
+                                   float* dt_o, float* t_o, int* anchors_o, void* feat_o_f16, void* stream) {
   if (n_rays <= 0) return F2B_OK;
-  compact_kernel<<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(keep, old_bounds, new_bounds, n_rays, pts, dirs,
-                                                                  dt, t, anchors, pts_o, dirs_o, dt_o, t_o, anchors_o);
+  F2B_REQUIRE(!feat_f16 || feat_o_f16, "f2b_compact_samples: feat_f16 without feat_o_f16");
+  compact_kernel<<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(keep, old_bounds, new_bounds, n_rays, pts, dirs, dt, t,
+                                                                  anchors, (const uint4*)feat_f16, pts_o, dirs_o, dt_o,
+                                                                  t_o, anchors_o, (uint4*)feat_o_f16);
   return check_launch("f2b_compact_samples");
 }
 

@@ -7,7 +7,9 @@
 // The 32 encoded halfs of a sample go from registers straight into the UMMA operand tile in shared
 // memory (SWIZZLE_64B K-major row of thread i == sample i); they reach HBM only when the backward pass
 // needs them (feat_save).  Modes:
-//   logit_only  — the no-grad early-stop pass (Renderer.cpp:107-126) needs only channel 0: 4 B/sample out;
+//   logit_only  — the no-grad early-stop pass (Renderer.cpp:107-126) needs only channel 0: 4 B/sample out
+//                 (+ optionally the encoded features, which the gradient pass re-uses for the surviving
+//                 samples instead of gathering the table a second time);
 //   full        — out [P,16] fp32 (fp16-rounded values, as TCNNWP::Query returns) + optional saves.
 // Per sample the kernel moves 16 B in + 512 B of L2 gathers; the MLP rides along on the tensor pipe.
 #include "common.cuh"
@@ -82,7 +84,7 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
     for (int c = 0; c < 4; c++) {
       const uint4 v = make_uint4(enc[4 * c], enc[4 * c + 1], enc[4 * c + 2], enc[4 * c + 3]);
       *reinterpret_cast<uint4*>(sm + FieldSmem::A0 + sw64_off(tid, c)) = v;
-      if (!LOGIT_ONLY && feat_save && valid) reinterpret_cast<uint4*>(feat_save + size_t(p) * 32)[c] = v;
+      if (feat_save && valid) reinterpret_cast<uint4*>(feat_save + size_t(p) * 32)[c] = v;
     }
     fence_async_smem();
     __syncthreads();
@@ -167,7 +169,7 @@ extern "C" int f2b_field_fwd(const void* table_f16, const int* prim_pool, const 
     cudaFuncSetAttribute(field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);
     field_fwd_kernel<true><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(
         (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, (const __half*)mlp_params_f16, pts, vol,
-        vol_stride, n_pts, out_f32, nullptr, nullptr);
+        vol_stride, n_pts, out_f32, (__half*)feat_save_f16, nullptr);
   } else {
     cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);
     field_fwd_kernel<false><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(

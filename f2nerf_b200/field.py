@@ -175,21 +175,28 @@ class Hash3DAnchored:
         self.mlp_.InitParams()
 
 
-def field_forward(field, table16, params16, points, anchors, anchor_stride, save, logit_only=False):
+def field_forward(field, table16, params16, points, anchors, anchor_stride, save, logit_only=False, save_feat=None):
     """hash encode -> MLP.  Returns (out, feat16, hidden); out is fp32 [n,16], or [n] (channel 0) when
-    ``logit_only``; feat16 / hidden only when ``save``.  With the tcgen05 MLP selected (default) this is ONE
-    fused kernel (f2b_field_fwd); with the CUDA-core twin it is encode + MLP + cast."""
+    ``logit_only``; feat16 when ``save`` or ``save_feat``, hidden only when ``save``.  With the tcgen05 MLP
+    selected (default) this is ONE fused kernel (f2b_field_fwd); with the CUDA-core twin it is encode + MLP + cast."""
     from . import _lib
+    save_feat = save if save_feat is None else save_feat
     if _lib.lib.f2b_get_mlp_impl() == 1 and field.mlp_.n_hidden_matmuls == 0:
         return ops.field_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, params16,
-                             points, anchors, anchor_stride, logit_only=logit_only, save=save)
+                             points, anchors, anchor_stride, logit_only=logit_only, save=save, save_feat=save_feat)
     feat16 = ops.hash_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, points,
                           anchors, anchor_stride)
-    out16, hidden = ops.mlp_fwd(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save)
+    out16, hidden = ops.mlp_fwd(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save and not logit_only)
     out = ops.cast_f16_to_f32(out16)
     if logit_only:
         out = out[:, 0].contiguous()
-    return out, (feat16 if save else None), hidden
+    return out, (feat16 if save_feat else None), hidden
+
+
+def field_forward_from_features(field, params16, feat16, save):
+    """MLP on already-encoded features (rows re-used from the early-stop pass): -> (out fp32 [n,16], hidden)."""
+    out16, hidden = ops.mlp_fwd(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save)
+    return ops.cast_f16_to_f32(out16), hidden
 
 
 def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidden, d_out_f32):

@@ -115,11 +115,13 @@ def hash_bwd(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, 
 
 
 def field_fwd(table_f16, prim_pool, bias_pool, n_volumes, local_size, params_f16, pts, vol, vol_stride=1, logit_only=False,
-              save=False):
-    """Fused hash encode + tcgen05 field MLP.  -> (out [n] or [n,16] fp32, feat16 | None, hidden | None)."""
+              save=False, save_feat=None):
+    """Fused hash encode + tcgen05 field MLP.  -> (out [n] or [n,16] fp32, feat16 | None, hidden | None).
+    ``save`` keeps features + hidden activations (gradient pass); ``save_feat`` keeps only the features."""
     n = pts.shape[0]
+    save_feat = save if save_feat is None else save_feat
     out = dev_empty((n,) if logit_only else (n, 16), F32, pts)
-    feat = dev_empty((n, 32), F16, pts) if (save and not logit_only) else None
+    feat = dev_empty((n, 32), F16, pts) if save_feat else None
     hidden = dev_empty((1, n, 64), F16, pts) if (save and not logit_only) else None
     call("f2b_field_fwd", table_f16, prim_pool, bias_pool, int(n_volumes), int(local_size), params_f16, pts, vol,
          int(vol_stride), n, int(bool(logit_only)), out, feat, hidden, stream())
@@ -209,11 +211,11 @@ def early_stop(logit, logit_stride, dt, bounds):
     return weights, alphas, keep, new_bounds, total
 
 
-def compact_samples(keep, old_bounds, new_bounds, n_kept, pts, dirs, dt, t, anchors):
+def compact_samples(keep, old_bounds, new_bounds, n_kept, pts, dirs, dt, t, anchors, feat=None, feat_out=None):
     outs = (dev_empty((n_kept, 3), F32, pts), dev_empty((n_kept, 3), F32, pts), dev_empty((n_kept,), F32, pts),
             dev_empty((n_kept,), F32, pts), dev_empty((n_kept, 3), I32, pts))
-    call("f2b_compact_samples", keep, old_bounds, new_bounds, old_bounds.shape[0], pts, dirs, dt, t, anchors, *outs,
-         stream())
+    call("f2b_compact_samples", keep, old_bounds, new_bounds, old_bounds.shape[0], pts, dirs, dt, t, anchors, feat, *outs,
+         feat_out, stream())
     return outs
 
 

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .field import field_backward, field_forward
+from .field import field_backward, field_forward, field_forward_from_features
 from .sampler import TRAIN, VALIDATE, SampleResultFlex
 
 N_EDGE_PTS = 8192
@@ -77,19 +77,28 @@ class Renderer:
         with torch.no_grad():
             table16 = field.table_f16()
             fparams16 = field.mlp_.params_f16()
-            logit_all, _, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False, logit_only=True)
+            # the encoded features of ALL samples are kept: survivors re-use them in the gradient pass instead of
+            # gathering the table a second time (identical values: same points, same table)
+            logit_all, feat_all, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False,
+                                                   logit_only=True, save_feat=True)
             weights0, alphas0, keep, new_bounds, total = ops.early_stop(logit_all, 1, sr.dt, sr.pts_idx_bounds)
             n_kept = int(total.item())                                               # sync 2
             if train:
                 sampler.UpdateOctNodes(sr, weights0, alphas0)
                 gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
+            n_edge = 2 * N_EDGE_PTS if train else 0
+            feat_q = torch.empty((n_kept + n_edge, 32), dtype=torch.float16, device=dev)
             pts, dirs, dt, t, anchors = ops.compact_samples(keep, sr.pts_idx_bounds, new_bounds, n_kept, sr.pts,
-                                                            sr.dirs, sr.dt, sr.t, sr.anchors)
+                                                            sr.dirs, sr.dt, sr.t, sr.anchors, feat_all, feat_q)
+            del feat_all
             es = SampleResultFlex(pts, dirs, dt, t, anchors, new_bounds, sr.first_oct_dis.clone())
             if train:                                                                 # TV-loss edge points
                 edge_pts, edge_anchors = sampler.GetEdgeSamples(N_EDGE_PTS)
-                q_pts = torch.cat([pts, edge_pts.reshape(N_EDGE_PTS * 2, 3)], 0)
-                q_anchors = torch.cat([anchors[:, 0], edge_anchors.reshape(N_EDGE_PTS * 2)], 0).contiguous()
+                e_pts, e_anc = edge_pts.reshape(N_EDGE_PTS * 2, 3), edge_anchors.reshape(N_EDGE_PTS * 2)
+                q_pts = torch.cat([pts, e_pts], 0)
+                q_anchors = torch.cat([anchors[:, 0], e_anc], 0).contiguous()
+                feat_q[n_kept:] = ops.hash_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_,
+                                               e_pts.contiguous(), e_anc.contiguous(), 1)
             else:
                 q_pts, q_anchors = pts, anchors[:, 0].contiguous()
             pt_emb_idx = ray_emb_idx = None
@@ -98,7 +107,7 @@ class Renderer:
                 pt_emb_idx = ops.scatter_idx(n_kept, new_bounds, ray_emb_idx)
 
         grad_on = torch.is_grad_enabled() and train
-        args = (self, es, q_pts, q_anchors, pt_emb_idx, ray_emb_idx, bg, table16, n_kept, grad_on)
+        args = (self, es, q_pts, q_anchors, pt_emb_idx, ray_emb_idx, bg, feat_q, n_kept, grad_on)
         colors, disparity, depth, weights, edge_feats = _RenderFunction.apply(
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, *args)
         if not train:
@@ -133,11 +142,11 @@ class _RenderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat_pool, field_params, shader_params, app_emb, renderer, es, q_pts, q_anchors, pt_emb_idx,
-                ray_emb_idx, bg, table16, n_kept, grad_on):
+                ray_emb_idx, bg, feat16, n_kept, grad_on):
         field, shader = renderer.scene_field_, renderer.shader_
         fparams16 = ops.cast_f32_to_f16(field_params)
         sparams16 = ops.cast_f32_to_f16(shader_params)
-        scene_feat, feat16, f_hidden = field_forward(field, table16, fparams16, q_pts, q_anchors, 1, save=grad_on)
+        scene_feat, f_hidden = field_forward_from_features(field, fparams16, feat16, save=grad_on)
         emb = app_emb if pt_emb_idx is not None else None
         mlp_in = ops.shader_prep(scene_feat[:n_kept], es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
             torch.empty((0, 32), dtype=torch.float16, device=bg.device)
@@ -157,7 +166,7 @@ class _RenderFunction(torch.autograd.Function):
         field, shader, gdp = renderer.scene_field_, renderer.shader_, renderer.global_data_pool_
         (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
          rgb) = ctx.pack
-        if feat16 is None:
+        if f_hidden is None:
             raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
         n_q, dev = q_pts.shape[0], q_pts.device
         n_rays = es.pts_idx_bounds.shape[0]

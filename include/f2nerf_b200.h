@@ -137,7 +137,7 @@ int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, voi
 
 /* Fused Hash3DAnchored::AnchoredQuery (Hash3DAnchored.cpp:84-99): hash encode + tcgen05 MLP(32->64->16) in one
  * kernel; the encoded features reach HBM only through feat_save (backward needs them).
- * logit_only != 0: the no-grad early-stop pass — out is [P] fp32 (channel 0 only), no saves.
+ * logit_only != 0: the no-grad early-stop pass — out is [P] fp32 (channel 0 only); feat_save optional, no hidden_save.
  * otherwise out is [P,16] fp32 (fp16-rounded values, as TCNNWP::Query returns); feat_save [P,32] fp16 and
  * hidden_save [P,64] fp16 are optional. */
 int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
@@ -196,12 +196,13 @@ int f2b_early_stop(const float* logit, int logit_stride, const float* dt, const 
                    int n_rays, float* weights, float* alphas, uint8_t* keep,
                    int* ray_counts /* [n_rays] caller-owned scratch */,
                    int* new_bounds /* [n_rays,2] */, int* total_kept /* [1] */, void* stream);
-/* Gather-compact the surviving samples (44 B/pt). */
+/* Gather-compact the surviving samples (44 B/pt) and, optionally, their encoded features (feat_f16 [P,32]
+ * from the early-stop pass -> feat_o_f16 [P',32]) so the gradient pass does not gather the table again. */
 int f2b_compact_samples(const uint8_t* keep, const int* old_bounds, const int* new_bounds, int n_rays,
                         const float* pts, const float* dirs, const float* dt, const float* t,
-                        const int* anchors,
+                        const int* anchors, const void* feat_f16 /* nullable */,
                         float* pts_o, float* dirs_o, float* dt_o, float* t_o, int* anchors_o,
-                        void* stream);
+                        void* feat_o_f16 /* nullable */, void* stream);
 /* Forward composite. logit: scene_feat[:,0] (stride logit_stride); rgb [P,3]; t is the raw sample t
  * (the +1e-2 of Renderer.cpp:197 is applied inside).  Outputs per ray: colors[3], disparity, depth;
  * per point: weights. */
