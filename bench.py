@@ -46,19 +46,25 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.err = index, [], False, None
-
-    def run(self):
-        try:
+        self.index, self.rows, self.stop_flag, self.err, self.h = index, [], False, None, None
+        try:                                     # nvmlInit takes ~0.3 s and a driver lock: do it before the timed region
             import pynvml as nv
             nv.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            idx = int(vis.split(",")[index]) if vis and vis.split(",")[0].isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)[:120]
+
+    def run(self):
+        if self.h is None:
+            return
+        import pynvml as nv
+        try:
             while not self.stop_flag:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h),
-                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
                 time.sleep(0.1)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)[:120]

@@ -22,6 +22,7 @@
 //    intra-group ordering is assumed), not 192 B/thread of local memory.
 #include "common.cuh"
 #include "scan.cuh"
+#include <stdlib.h>
 
 namespace f2b {
 
@@ -295,6 +296,162 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 16-lane variant: one perspective projection per lane (lanes 0..11 of a half-warp; 12..15 idle), two rays per
+// warp => 4x the warps of the 4-lane kernel (the march is latency bound: at 4 lanes/ray 4096 rays are only 512
+// warps on 592 SM sub-partitions) and a 3x shorter instruction stream per step.  The 12-term mixing sums keep
+// the reference's tree: lane 3s+2 forms w*t, lane 3s+1 and 3s fold their term in with one fma each
+// (g_s = fma(w0,t0, fma(w1,t1, w2*t2))), lanes 0 and 6 add their neighbour group (g0+g1, g2+g3), lane 0 adds the
+// halves — 4 shuffles per value, bit-identical to the reference's unrolled redux.  Lane 0 of the half-warp then
+// derives the step and broadcasts it; every lane advances t / walks the octree redundantly (private DFS stack).
+constexpr int kL16 = 16;
+constexpr int kRaysPerBlock16 = 2;
+
+__device__ __forceinline__ float tree12(float w, float tv, int role) {
+  // role = g % 3 for g < 12; returns the full 12-term sum in lane 0 of the half-warp (garbage elsewhere)
+  const float m = fmul(w, tv);
+  const float a1 = __shfl_down_sync(0xffffffffu, m, 1, 16);
+  const float v1 = role == 1 ? ffma(w, tv, a1) : m;
+  const float a2 = __shfl_down_sync(0xffffffffu, v1, 1, 16);
+  const float v0 = ffma(w, tv, a2);                                  // meaningful in lanes 0,3,6,9
+  const float b = __shfl_down_sync(0xffffffffu, v0, 3, 16);
+  const float sg = fadd(v0, b);                                      // lanes 0 and 6
+  const float c = __shfl_down_sync(0xffffffffu, sg, 6, 16);
+  return fadd(sg, c);                                                // lane 0
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32)
+march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ trans,
+               const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+               const float* __restrict__ rays_noise, int n_rays, float near0, float far0,
+               float sample_l, int scale_by_dis, int max_hits, int count_all_hits,
+               int* __restrict__ ray_counts, int* __restrict__ total_hits, const int* __restrict__ bounds,
+               float* __restrict__ o_pts, float* __restrict__ o_dirs, float* __restrict__ o_dt,
+               float* __restrict__ o_t, int* __restrict__ o_anchors, float* __restrict__ first_oct_dis) {
+  __shared__ int s_stack[32 * kStackPitch];
+  const int lane = threadIdx.x;
+  const int g = lane & 15;                          // lane inside the ray's half-warp
+  const int pi = g < 12 ? g : 11;                   // my projection (idle lanes shadow 11)
+  const int role = g % 3;
+  int ray = blockIdx.x * kRaysPerBlock16 + (lane >> 4);
+  const bool active = ray < n_rays;
+  if (!active) ray = n_rays - 1;
+  constexpr bool FILL = MODE != 0;
+
+  const float o[3] = {__ldg(rays_o + ray * 3), __ldg(rays_o + ray * 3 + 1), __ldg(rays_o + ray * 3 + 2)};
+  const float d[3] = {__ldg(rays_d + ray * 3), __ldg(rays_d + ray * 3 + 1), __ldg(rays_d + ray * 3 + 2)};
+  const float* noise = rays_noise + ray;
+  Dfs dfs;
+  dfs.stack = s_stack + lane * kStackPitch;
+  dfs.sp = 0; dfs.n_hits = 0; dfs.max_hits = max_hits;
+  dfs.st = (int(d[0] > 0.f) << 2) | (int(d[1] > 0.f) << 1) | int(d[2] > 0.f);
+  dfs.stack[0] = 0;
+
+  int cap = F2B_MAX_SAMPLE_PER_RAY;
+  size_t out_base = 0;
+  if (MODE == 1) { out_base = bounds[ray * 2]; cap = bounds[ray * 2 + 1] - int(out_base); }
+  else if (MODE == 2) out_base = size_t(ray) * F2B_MAX_SAMPLE_PER_RAY;
+
+  Hit hit;
+  hit.node = 0; hit.trans_idx = 0; hit.near = 0.f; hit.far = 0.f;
+  bool have = next_hit(dfs, nodes, o, d, near0, far0, hit);
+  if (FILL && active && g == 0) first_oct_dis[ray] = have ? hit.near : 1e9f;
+
+  int k = 0;
+  float t = hit.near, far = hit.far;
+  int cur_node = hit.node, cur_trans = hit.trans_idx, loaded_trans = -1;
+  bool first = true;
+  float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 1.f}, pw[3] = {0.f, 0.f, 0.f};
+  float rclip = 1.f;
+  bool running = have && cap > 0;
+  while (__any_sync(0xffffffffu, running)) {
+    if (running && cur_trans != loaded_trans) {
+      const TransInfo* T = trans + cur_trans;
+      const float4 ra = __ldg(reinterpret_cast<const float4*>(&T->w2xz[pi][0]));
+      const float4 rb = __ldg(reinterpret_cast<const float4*>(&T->w2xz[pi][4]));
+      pa[0] = ra.x; pa[1] = ra.y; pa[2] = ra.z; pa[3] = ra.w;
+      pb[0] = rb.x; pb[1] = rb.y; pb[2] = rb.z; pb[3] = rb.w;
+#pragma unroll
+      for (int r = 0; r < 3; r++) pw[r] = __ldg(&T->weight[r][pi]);
+      const float4 cd = __ldg(reinterpret_cast<const float4*>(&T->center[0]));
+      const float ex = fsub(o[0], cd.x), ey = fsub(o[1], cd.y), ez = fsub(o[2], cd.z);
+      rclip = fmaxf(fdiv(fsqrt(ffma(ex, ex, ffma(ey, ey, fmul(ez, ez)))), cd.w), 1.f);
+      loaded_trans = cur_trans;
+    }
+    const float X = ffma(t, d[0], o[0]), Y = ffma(t, d[1], o[1]), Z = ffma(t, d[2], o[2]);
+    const float xz0 = fadd(ffma(X, pa[0], fmul(Y, pa[1])), ffma(Z, pa[2], pa[3]));
+    const float xz1 = fadd(ffma(X, pb[0], fmul(Y, pb[1])), ffma(Z, pb[2], pb[3]));
+    const float rr = frcp(xz1);
+    const float q = fdiv(-xz0, fmul(xz1, xz1));
+    const float T0 = ffma(pa[0], rr, fmul(pb[0], q));
+    const float T1 = ffma(rr, pa[1], fmul(q, pb[1]));
+    const float T2 = ffma(rr, pa[2], fmul(q, pb[2]));
+    float proj[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const float j0 = tree12(pw[r], T0, role), j1 = tree12(pw[r], T1, role), j2 = tree12(pw[r], T2, role);
+      proj[r] = ffma(j0, d[0], ffma(j1, d[1], fmul(j2, d[2])));
+    }
+    float w[3] = {0.f, 0.f, 0.f};
+    if (FILL) {
+      const float V = fdiv(xz0, xz1);
+#pragma unroll
+      for (int r = 0; r < 3; r++) w[r] = tree12(pw[r], V, role);
+    }
+    // leader (lane 0 of the half-warp) holds the true sums; everybody computes, the leader's values are broadcast
+    float den = fadd(fsqrt(ffma(proj[0], proj[0], ffma(proj[1], proj[1], fmul(proj[2], proj[2])))), 1e-6f);
+    float step = fdiv(fmul(sample_l, __ldg(noise + k)), den);
+    if (scale_by_dis) step = fmul(rclip, step);
+    den = __shfl_sync(0xffffffffu, den, 0, 16);
+    step = __shfl_sync(0xffffffffu, step, 0, 16);
+
+    if (running) {
+      if (!first) {
+        if (FILL && active) {
+          const size_t idx = out_base + k;
+          if (g == 0) {
+            o_pts[idx * 3] = w[0]; o_pts[idx * 3 + 1] = w[1]; o_pts[idx * 3 + 2] = w[2];
+          } else if (g == 1) {
+            if (MODE == 1) { o_dirs[idx * 3] = d[0]; o_dirs[idx * 3 + 1] = d[1]; o_dirs[idx * 3 + 2] = d[2]; }
+          } else if (g == 2) {
+            o_dt[idx] = fmul(step, den);
+            o_t[idx] = t;
+          } else if (g == 3) {
+            if (MODE == 1) { o_anchors[idx * 3] = cur_trans; o_anchors[idx * 3 + 1] = cur_node; o_anchors[idx * 3 + 2] = 0; }
+            else { o_anchors[idx * 2] = cur_trans; o_anchors[idx * 2 + 1] = cur_node; }
+          }
+        }
+        k++;
+      }
+      float tn = fadd(t, step);
+      if (tn > far) {
+        for (;;) {
+          have = next_hit(dfs, nodes, o, d, near0, far0, hit);
+          if (!have) break;
+          far = hit.far; cur_node = hit.node; cur_trans = hit.trans_idx;
+          const float nf = ceilf(fmaxf(fdiv(fsub(hit.near, t), step), 1.f));
+          const int n = (int)nf;
+          tn = ffma(step, (float)n, t);
+          if (!(tn > far)) break;
+        }
+      }
+      t = tn;
+      first = false;
+      running = (k < cap) && have;
+    }
+  }
+  if (MODE != 1) {
+    if (count_all_hits) {
+      while (next_hit(dfs, nodes, o, d, near0, far0, hit)) {}
+    }
+    if (active && g == 0) {
+      ray_counts[ray] = k;
+      if (dfs.n_hits) atomicAdd(total_hits, dfs.n_hits);
+    }
+  }
+}
+
 // Second half of the one-pass sampler: copy each ray's samples from its scratch slot to the compact,
 // ray-ordered outputs (the reference's cumsum layout), regenerating dirs / anchors[:,2]; warp per ray.
 __global__ void __launch_bounds__(256)
@@ -444,6 +601,17 @@ __global__ void update_stats_kernel(int n_nodes, const int* __restrict__ vote_w,
 
 using namespace f2b;
 
+static int march_lanes() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("F2B_MARCH_LANES"); v = (e && atoi(e) == 4) ? 4 : 16; }
+  return v;
+}
+#define F2B_LAUNCH_MARCH(MODE, st, ...)                                                                   \
+  do {                                                                                                    \
+    if (march_lanes() == 4) march_kernel<MODE><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(__VA_ARGS__); \
+    else march16_kernel<MODE><<<div_up(n_rays, kRaysPerBlock16), 32, 0, st>>>(__VA_ARGS__);               \
+  } while (0)
+
 extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
                                  const float* rays_o, const float* rays_d, const float* rays_noise,
                                  int n_rays, float near, float far, float sample_l, int scale_by_dis,
@@ -456,7 +624,7 @@ extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void
   if (n_rays == 0) return check_launch("f2b_sampler_count");      // empty batch: totals = {0, 0}
   F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && ray_counts && pts_idx_bounds,
               "f2b_sampler_count: null pointer");
-  march_kernel<0><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
+  F2B_LAUNCH_MARCH(0, st,
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
       far, sample_l, scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, nullptr,
       nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -473,7 +641,7 @@ extern "C" int f2b_sampler_fill(const void* tree_nodes, int n_nodes, const void*
   F2B_REQUIRE(n_rays >= 0 && n_nodes > 0, "f2b_sampler_fill: bad sizes");
   if (n_rays == 0) return F2B_OK;
   F2B_REQUIRE(tree_nodes && trans && pts_idx_bounds && first_oct_dis, "f2b_sampler_fill: null pointer");
-  march_kernel<1><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, as_stream(stream)>>>(
+  F2B_LAUNCH_MARCH(1, as_stream(stream),
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near,
       far, sample_l, scale_by_dis, max_oct_intersect_per_ray, 0, nullptr, nullptr, pts_idx_bounds, pts,
       dirs, dt, t, anchors, first_oct_dis);
@@ -493,7 +661,7 @@ extern "C" int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void
   if (n_rays == 0) return check_launch("f2b_sampler_march");
   F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && s_pts && s_dt && s_t && s_anchors && ray_counts &&
               pts_idx_bounds && first_oct_dis, "f2b_sampler_march: null pointer");
-  march_kernel<2><<<div_up(n_rays, kRaysPerBlock), kRaysPerBlock * kLanesPerRay, 0, st>>>(
+  F2B_LAUNCH_MARCH(2, st,
       (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l,
       scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, s_pts, nullptr, s_dt, s_t,
       s_anchors, first_oct_dis);
