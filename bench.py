@@ -168,19 +168,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value): K steps bracketed by barrier + synchronize, CUDA events --------
+    clocks = ClockSampler(local)                 # polling starts before the warm-up: the first NVML queries of a
+    clocks.start()                               # process stall kernel submission for 100s of ms on this driver
     for _ in range(args.warmup):
         train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
-    clocks = ClockSampler(local)
-    clocks.start()
     barrier()
+    clocks.rows.clear()                          # keep only samples taken under the timed regions
     launches0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     n_samples = n_kept = 0
+    walls = []
     for _ in range(args.steps):
+        w0 = time.perf_counter()
         loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
         n_samples += prob["renderer"].sample_result_.pts.shape[0]
         n_kept += res.weights.shape[0]
+        walls.append(round((time.perf_counter() - w0) * 1e3, 2))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -249,6 +253,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in (h_o, h_d, h_cam, h_gt))) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "host_wall_ms_per_step": walls,
         "clocks": clocks.summary(),
         "roofline": roof,
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in

@@ -108,4 +108,29 @@ def render_train(sc, rays_o, rays_dn, noise, bg, field, shader_params, app_emb=N
                                                   np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32),
                                                   1.0 / LOSS_SCALE, field["table16"].shape[0], half_products=2)
     out["d_scene"] = d_scene
+    # --- tiny-cuda-nn style emulation: fp16 accumulators in the field MLP's input gradient (wmma half fragments),
+    # then fp16 products + fp16 accumulation in the scatter.  Statistical stand-in for the reference's own noise.
+    dout16 = f16(d_scene * LOSS_SCALE)
+    din_half = mlp_bwd_half_accum(dout16, np.asarray(f_hid).reshape(-1, 64), fp16)
+    out["grad_feat_pool_tcnn_emulation"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
+                                                      np.ascontiguousarray(q_pts), q_vol, 1, din_half.astype(np.float32),
+                                                      1.0 / LOSS_SCALE, field["table16"].shape[0], half_products=2)
+    a_out, a_in = np.abs(dout16.astype(np.float32)), np.abs(d_feat16.astype(np.float32))
+    out["grad_magnitudes"] = dict(dout16_median=float(np.median(a_out[a_out > 0])) if (a_out > 0).any() else 0.0,
+                                  dout16_frac_zero=float((a_out == 0).mean()), dout16_frac_subnormal=float((a_out < 6.1e-5).mean()),
+                                  din16_median=float(np.median(a_in[a_in > 0])) if (a_in > 0).any() else 0.0,
+                                  din16_frac_zero=float((a_in == 0).mean()), din16_frac_subnormal=float((a_in < 6.1e-5).mean()))
     return out
+
+
+def mlp_bwd_half_accum(dout16, hidden16, params16):
+    """Field MLP (32 -> 64 -> 16, no bias) input gradient with an fp16 accumulator rounded after every 16-wide
+    k-step, as tiny-cuda-nn's wmma<half accumulator> fragments do (fully_fused_mlp.cu:150-259)."""
+    W0 = params16[:64 * 32].reshape(64, 32).astype(np.float32)
+    Wo = params16[64 * 32:64 * 32 + 16 * 64].reshape(16, 64).astype(np.float32)
+    dh = f16(dout16.astype(np.float32) @ Wo)                     # K = 16: one k-step
+    dh = np.where(hidden16 > 0, dh, np.float16(0))
+    acc = np.zeros((dout16.shape[0], 32), np.float16)
+    for c in range(4):                                           # K = 64: four k-steps
+        acc = f16(acc.astype(np.float32) + dh[:, 16 * c:16 * c + 16].astype(np.float32) @ W0[16 * c:16 * c + 16])
+    return acc

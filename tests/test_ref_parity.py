@@ -142,6 +142,10 @@ def test_render_train_vs_reference(ref):
     assert abs(float(loss) - float(ref["train_loss"][0])) <= 5e-3 * abs(float(ref["train_loss"][0]))
     assert np.abs(N(r.colors) - ref["train_colors"]).max() <= 0.03
     summary = {}
+    if "train_edge_feats" in ref:                     # same Philox draws => same edge points => same features (fp16 MLP noise)
+        ef_m, ef_t = N(r.edge_feats).astype(np.float64), ref["train_edge_feats"].astype(np.float64)
+        summary["edge_feats"] = dict(max_abs=float(np.abs(ef_m - ef_t).max()), ref_abs_max=float(np.abs(ef_t).max()),
+                                     cos=float((ef_m * ef_t).sum() / (np.linalg.norm(ef_m) * np.linalg.norm(ef_t) + 1e-30)))
     for name, mine, theirs in (("field_mlp", field.mlp_.params_.grad, ref["grad_field_mlp"]),
                                ("shader_mlp", shader.mlp_.params_.grad, ref["grad_shader_mlp"]),
                                ("app_emb", renderer.app_emb_.grad, ref["grad_app_emb"]),
@@ -170,12 +174,17 @@ def test_render_train_vs_reference(ref):
     summary["feat_pool_oracle_halfprod_vs_ref"] = cosd(orc["grad_feat_pool_half_products"], gref)
     summary["feat_pool_oracle_halfaccum_vs_ref"] = cosd(orc["grad_feat_pool_half_accum"], gref)
     summary["feat_pool_ours_vs_oracle_exact"] = cosd(N(field.feat_pool_.grad), orc["grad_feat_pool"])
+    summary["feat_pool_tcnn_emulation_vs_exact"] = cosd(orc["grad_feat_pool_tcnn_emulation"], orc["grad_feat_pool"])
+    summary["feat_pool_tcnn_emulation_vs_ref"] = cosd(orc["grad_feat_pool_tcnn_emulation"], gref)
+    summary["grad_magnitudes_x128"] = orc["grad_magnitudes"]
     S = field.local_size_                                    # per level-slab agreement (fp32 element ranges [l*S, (l+2)*S))
     mine_flat, ex_flat = N(field.feat_pool_.grad).reshape(-1).astype(np.float64), np.asarray(orc["grad_feat_pool"]).reshape(-1)
+    em_flat = np.asarray(orc["grad_feat_pool_tcnn_emulation"]).reshape(-1)
     slabs = []
     for l in range(17):
         sl = slice(l * S, (l + 1) * S)
         slabs.append(dict(slab=l, cos_ours_ref=cosd(mine_flat[sl], gref[sl]), cos_ours_exact=cosd(mine_flat[sl], ex_flat[sl]),
+                          cos_emul_exact=cosd(em_flat[sl], ex_flat[sl]), cos_emul_ref=cosd(em_flat[sl], gref[sl]),
                           norm_ref=float(np.linalg.norm(gref[sl])), norm_ours=float(np.linalg.norm(mine_flat[sl])),
                           nnz_ref=int((gref[sl] != 0).sum()), nnz_ours=int((mine_flat[sl] != 0).sum())))
     summary["feat_pool_slabs"] = slabs
