@@ -65,6 +65,7 @@ SIGNATURES = {
     "f2b_shader_act": [_P, c_int, _P, _P],
     "f2b_shader_act_bwd": [_P, _P, c_int, c_float, _P, _P],
     "f2b_shader_prep_bwd": [_P, _P, _P, c_int, c_float, _P, _P, _P],
+    "f2b_shader_prep_bwd_f16": [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P],
     "f2b_early_stop": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
     "f2b_compact_samples": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_composite_fwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],

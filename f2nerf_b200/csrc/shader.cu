@@ -124,46 +124,57 @@ __global__ void shader_act_bwd_kernel(const __half* __restrict__ raw, const floa
 // (ScatterAddFuncBackwardBlock, Scatter.cu:23-40 — there a dense [n_emb x n_blocks] compare-and-sum).  The
 // camera index is constant along a ray, so the sum is a register accumulation + one warp reduction + 16
 // atomicAdds per ray instead of one atomic per sample and channel.
+// Lane mapping: 4 lanes per sample (4 channels each), 8 samples per warp pass — every load is a full 32 B
+// sector of the row and every store instruction covers whole rows.
+// F16OUT: instead of the fp32 gradient the kernel emits what TCNNWPFunction::backward (TCNNWP.cpp:213-216)
+// makes of it one call later, half((d/loss_scale_shader) * loss_scale_field), with channel 0 taken from the
+// composite backward's d logit — the fp32 [P,16] round trip through HBM and its zero-fill disappear.
+template <bool F16OUT>
 __global__ void __launch_bounds__(256)
-shader_prep_bwd_kernel(const __half* __restrict__ d_mlp_in, const int* __restrict__ bounds,
-                       const int* __restrict__ emb_idx, int n_rays, float inv_loss_scale,
-                       float* __restrict__ d_scene_feat, float* __restrict__ d_app_emb) {
+shader_prep_bwd_kernel(const __half* __restrict__ d_mlp_in, const float* __restrict__ d_logit,
+                       const int* __restrict__ bounds, const int* __restrict__ emb_idx, int n_rays,
+                       float inv_loss_scale, float out_scale, float* __restrict__ d_scene_feat,
+                       __half* __restrict__ d_out16, float* __restrict__ d_app_emb) {
   const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ray >= n_rays) return;
   const int beg = bounds[2 * ray], end = bounds[2 * ray + 1];
-  float acc[16];
+  const int sub = lane & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = beg + (lane >> 2); i < end; i += 8) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(d_mlp_in + size_t(i) * 32) + sub);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    float g[4] = {f0.x * inv_loss_scale, f0.y * inv_loss_scale, f1.x * inv_loss_scale, f1.y * inv_loss_scale};
 #pragma unroll
-  for (int k = 0; k < 16; k++) acc[k] = 0.f;
-  for (int i = beg + lane; i < end; i += 32) {
-    const uint4* s = reinterpret_cast<const uint4*>(d_mlp_in + size_t(i) * 32);
-    float g[16];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const uint4 r = __ldg(s + q);
-      const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-      for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); g[8 * q + 2 * k] = f.x * inv_loss_scale; g[8 * q + 2 * k + 1] = f.y * inv_loss_scale; }
+    for (int k = 0; k < 4; k++) acc[k] += g[k];
+    if (F16OUT) {
+      if (sub == 0) g[0] = __ldg(d_logit + i);
+      const __half2 h0 = __floats2half2_rn(g[0] * out_scale, g[1] * out_scale);
+      const __half2 h1 = __floats2half2_rn(g[2] * out_scale, g[3] * out_scale);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(d_out16 + size_t(i) * 16)[sub] = o;
+    } else {
+      float* dst = d_scene_feat + size_t(i) * 16 + 4 * sub;
+      if (sub == 0) { dst[1] = g[1]; dst[2] = g[2]; dst[3] = g[3]; }
+      else *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
     }
-    float* dst = d_scene_feat + size_t(i) * 16;
-#pragma unroll
-    for (int k = 1; k < 16; k++) dst[k] = g[k];
-#pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] += g[k];
   }
   if (d_app_emb) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < 4; k++) {
       float v = acc[k];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
       acc[k] = v;
     }
-    if (lane < 16 && end > beg) {
-      float v = acc[0];
+    if (lane < 4 && end > beg) {
+      float* dst = d_app_emb + size_t(emb_idx[ray]) * 16 + 4 * sub;
 #pragma unroll
-      for (int k = 1; k < 16; k++) v = (lane == k) ? acc[k] : v;
-      atomicAdd(d_app_emb + size_t(emb_idx[ray]) * 16 + lane, v);
+      for (int k = 0; k < 4; k++) atomicAdd(dst + k, acc[k]);
     }
   }
 }
@@ -214,7 +225,19 @@ extern "C" int f2b_shader_prep_bwd(const void* d_mlp_in_f16, const int* pts_idx_
   if (n_rays <= 0) return F2B_OK;
   F2B_REQUIRE(d_mlp_in_f16 && pts_idx_bounds && d_scene_feat, "f2b_shader_prep_bwd: null pointer");
   F2B_REQUIRE(!d_app_emb || emb_idx, "f2b_shader_prep_bwd: d_app_emb without emb_idx");
-  shader_prep_bwd_kernel<<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(
-      (const __half*)d_mlp_in_f16, pts_idx_bounds, emb_idx, n_rays, inv_loss_scale, d_scene_feat, d_app_emb);
+  shader_prep_bwd_kernel<false><<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(
+      (const __half*)d_mlp_in_f16, nullptr, pts_idx_bounds, emb_idx, n_rays, inv_loss_scale, 1.f, d_scene_feat, nullptr, d_app_emb);
   return check_launch("f2b_shader_prep_bwd");
+}
+
+extern "C" int f2b_shader_prep_bwd_f16(const void* d_mlp_in_f16, const float* d_logit, const int* pts_idx_bounds,
+                                       const int* emb_idx, int n_rays, float inv_loss_scale, float field_loss_scale,
+                                       void* d_field_out_f16, float* d_app_emb, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(d_mlp_in_f16 && d_logit && pts_idx_bounds && d_field_out_f16, "f2b_shader_prep_bwd_f16: null pointer");
+  F2B_REQUIRE(!d_app_emb || emb_idx, "f2b_shader_prep_bwd_f16: d_app_emb without emb_idx");
+  shader_prep_bwd_kernel<true><<<div_up(int64_t(n_rays) * 32, 256), 256, 0, as_stream(stream)>>>(
+      (const __half*)d_mlp_in_f16, d_logit, pts_idx_bounds, emb_idx, n_rays, inv_loss_scale, field_loss_scale, nullptr,
+      (__half*)d_field_out_f16, d_app_emb);
+  return check_launch("f2b_shader_prep_bwd_f16");
 }

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .rng import burn_mlp_output
 
 N_LEVELS, N_CHANNELS = 16, 2
 LOSS_SCALE = 128.0
@@ -71,6 +72,7 @@ class _MLPFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, params, mlp):
+        burn_mlp_output(x.shape[0], x.device)                    # TCNNWP.cpp:143: the reference's output is a torch::rand
         x16 = ops.cast_f32_to_f16(x)
         p16 = ops.cast_f32_to_f16(params)
         need = x.requires_grad or params.requires_grad
@@ -199,14 +201,22 @@ def field_forward_from_features(field, params16, feat16, save):
     return ops.cast_f16_to_f32(out16), hidden
 
 
-def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidden, d_out_f32):
-    """dL/d out [n,16] fp32 -> (dL/d feat_pool fp32 [pool,2], dL/d mlp params fp32, finite flag tensor)."""
+def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidden, d_out_f32, d_out_f16=None, segments=None):
+    """dL/d out [n,16] (fp32, or already ``half(d * loss_scale)`` in ``d_out_f16``) ->
+    (dL/d feat_pool fp32 [pool,2], dL/d mlp params fp32).
+    ``segments``: optional list of (points, anchors, anchor_stride, first_row, n_rows) covering the rows of
+    ``feat16`` — the scatter then runs once per segment into the same table gradient, so callers holding the
+    query in pieces (ray samples + edge points) need not concatenate them."""
     scale = field.mlp_.loss_scale_
-    d16 = ops.cast_f32_to_f16(d_out_f32, scale)
+    d16 = d_out_f16 if d_out_f16 is not None else ops.cast_f32_to_f16(d_out_f32, scale)
     dfeat16, dparams = ops.mlp_bwd(d16, feat16, hidden, params16, field.mlp_.n_hidden_matmuls, need_din=True)
     grad_table = torch.zeros_like(field.feat_pool_)
-    ops.hash_bwd(field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, points, anchors, anchor_stride,
-                 dfeat16, 1.0 / scale, grad_table)
+    if segments is None:
+        segments = [(points, anchors, anchor_stride, 0, dfeat16.shape[0])]
+    for pts, anc, stride, first, rows in segments:
+        if rows > 0:
+            ops.hash_bwd(field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_, pts, anc, stride,
+                         dfeat16[first:first + rows], 1.0 / scale, grad_table)
     dparams = dparams / scale
     return grad_table, dparams
 
@@ -214,6 +224,7 @@ def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidd
 class _FieldFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_pool, params, points, anchors, field):
+        burn_mlp_output(points.shape[0], points.device)          # the MLP inside AnchoredQuery (TCNNWP.cpp:143)
         table16 = ops.table_to_half(feat_pool)
         params16 = ops.cast_f32_to_f16(params)
         need = feat_pool.requires_grad or params.requires_grad

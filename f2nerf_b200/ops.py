@@ -198,6 +198,13 @@ def shader_prep_bwd(d_mlp_in_f16, bounds, emb_idx, inv_loss_scale, d_scene_feat,
          d_app_emb, stream())
 
 
+def shader_prep_bwd_f16(d_mlp_in_f16, d_logit, bounds, emb_idx, inv_loss_scale, field_loss_scale, d_field_out_f16, d_app_emb):
+    """Fused tail of the shader backward: writes the field MLP's dL/dout (fp16, loss-scaled) for the first
+    len(d_logit) rows of ``d_field_out_f16`` and accumulates d_app_emb."""
+    call("f2b_shader_prep_bwd_f16", d_mlp_in_f16, d_logit, bounds, emb_idx, bounds.shape[0], float(inv_loss_scale),
+         float(field_loss_scale), d_field_out_f16, d_app_emb, stream())
+
+
 # ------------------------------------------------------------------ composite -------------------
 def early_stop(logit, logit_stride, dt, bounds):
     R, P = bounds.shape[0], dt.shape[0]

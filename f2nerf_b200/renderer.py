@@ -14,6 +14,7 @@ import torch
 
 from . import ops
 from .field import field_backward, field_forward, field_forward_from_features
+from .rng import burn_mlp_output, burn_rand
 from .sampler import TRAIN, VALIDATE, SampleResultFlex
 
 N_EDGE_PTS = 8192
@@ -79,6 +80,7 @@ class Renderer:
             fparams16 = field.mlp_.params_f16()
             # the encoded features of ALL samples are kept: survivors re-use them in the gradient pass instead of
             # gathering the table a second time (identical values: same points, same table)
+            burn_mlp_output(n_all, dev)                   # RNG parity: the reference's MLP output is a torch::rand (rng.py)
             logit_all, feat_all, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False,
                                                    logit_only=True, save_feat=True)
             weights0, alphas0, keep, new_bounds, total = ops.early_stop(logit_all, 1, sr.dt, sr.pts_idx_bounds)
@@ -95,19 +97,21 @@ class Renderer:
             if train:                                                                 # TV-loss edge points
                 edge_pts, edge_anchors = sampler.GetEdgeSamples(N_EDGE_PTS)
                 e_pts, e_anc = edge_pts.reshape(N_EDGE_PTS * 2, 3), edge_anchors.reshape(N_EDGE_PTS * 2)
-                q_pts = torch.cat([pts, e_pts], 0)
-                q_anchors = torch.cat([anchors[:, 0], e_anc], 0).contiguous()
+                e_pts, e_anc = e_pts.contiguous(), e_anc.contiguous()
                 feat_q[n_kept:] = ops.hash_fwd(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_,
-                                               e_pts.contiguous(), e_anc.contiguous(), 1)
+                                               e_pts, e_anc, 1)
+                segments = [(pts, anchors, 3, 0, n_kept), (e_pts, e_anc, 1, n_kept, n_edge)]
             else:
-                q_pts, q_anchors = pts, anchors[:, 0].contiguous()
+                segments = [(pts, anchors, 3, 0, n_kept)]
+            burn_mlp_output(n_kept + n_edge, dev)         # second AnchoredQuery (Renderer.cpp:165/172) ...
+            burn_mlp_output(n_kept, dev)                  # ... and the shader MLP (SHShader.cpp:27)
             pt_emb_idx = ray_emb_idx = None
             if train and self.use_app_emb_:
                 ray_emb_idx = emb_idx.to(torch.int32).contiguous()
                 pt_emb_idx = ops.scatter_idx(n_kept, new_bounds, ray_emb_idx)
 
         grad_on = torch.is_grad_enabled() and train
-        args = (self, es, q_pts, q_anchors, pt_emb_idx, ray_emb_idx, bg, feat_q, n_kept, grad_on)
+        args = (self, es, segments, None, pt_emb_idx, ray_emb_idx, bg, feat_q, n_kept, grad_on)
         colors, disparity, depth, weights, edge_feats = _RenderFunction.apply(
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, *args)
         if not train:
@@ -168,28 +172,37 @@ class _RenderFunction(torch.autograd.Function):
          rgb) = ctx.pack
         if f_hidden is None:
             raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
-        n_q, dev = q_pts.shape[0], q_pts.device
+        segments = q_pts
+        n_q, dev = feat16.shape[0], feat16.device
         n_rays = es.pts_idx_bounds.shape[0]
         zeros = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         d_colors = d_colors.contiguous() if d_colors is not None else zeros(n_rays, 3)
         d_disp = d_disp.contiguous() if d_disp is not None else None
         d_depth = d_depth.contiguous() if d_depth is not None else None
         d_weights = d_weights.contiguous() if d_weights is not None else None
-        d_scene = zeros(n_q, 16)
-        if d_edge is not None:
-            d_scene[n_kept:] = d_edge.reshape(-1, 16)
-        # composite (+TruncExp, +GradientScaling) -> d logit (column 0 of d_scene), d rgb
+        if ctx.gs_progress < 1.:                          # GradientScaling::backward draws an unused rand_like (CustomOps.cu:154)
+            burn_rand(n_kept * 3, dev)
+            burn_rand(n_kept, dev)
+        # composite (+TruncExp, +GradientScaling) -> d logit, d rgb
+        d_logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
         d_rgb = ops.composite_bwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg, d_colors, d_disp, d_depth,
-                                  d_weights, ctx.gs_progress, d_scene, 16)
-        # shader: sigmoid -> MLP -> input assembly
-        s_scale = shader.mlp_.loss_scale_
+                                  d_weights, ctx.gs_progress, d_logit, 1)
+        # shader: sigmoid -> MLP -> input assembly; the last kernel writes the field MLP's fp16 dL/dout directly
+        s_scale, f_scale = shader.mlp_.loss_scale_, field.mlp_.loss_scale_
         d_raw = ops.shader_act_bwd(raw, d_rgb, s_scale)
         d_in16, d_sparams = ops.mlp_bwd(d_raw, mlp_in, s_hidden, sparams16, shader.mlp_.n_hidden_matmuls, need_din=True)
         d_sparams = d_sparams / s_scale
         d_app = torch.zeros_like(renderer.app_emb_) if ray_emb_idx is not None else None
-        ops.shader_prep_bwd(d_in16, es.pts_idx_bounds, ray_emb_idx, 1.0 / s_scale, d_scene, d_app)
+        d_scene16 = torch.empty((n_q, 16), dtype=torch.float16, device=dev)
+        if n_q > n_kept:
+            if d_edge is not None:
+                d_scene16[n_kept:] = (d_edge.reshape(-1, 16) * f_scale).to(torch.float16)
+            else:
+                d_scene16[n_kept:].zero_()
+        ops.shader_prep_bwd_f16(d_in16, d_logit, es.pts_idx_bounds, ray_emb_idx, 1.0 / s_scale, f_scale, d_scene16, d_app)
         # field: MLP -> hash scatter
-        d_table, d_fparams = field_backward(field, fparams16, q_pts, q_anchors, 1, feat16, f_hidden, d_scene)
+        d_table, d_fparams = field_backward(field, fparams16, None, None, 1, feat16, f_hidden, None, d_out_f16=d_scene16,
+                                            segments=segments)
         # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
         bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
         renderer.nonfinite_flag_ = bad

@@ -183,6 +183,13 @@ int f2b_shader_act_bwd(const void* raw_out_f16, const float* d_rgb, int n_pts, f
 int f2b_shader_prep_bwd(const void* d_mlp_in_f16 /* [P,32] */, const int* pts_idx_bounds /* [R,2] */,
                         const int* emb_idx /* [R] or NULL */, int n_rays, float inv_loss_scale,
                         float* d_scene_feat /* [P,16] */, float* d_app_emb /* [n_emb,16] or NULL */, void* stream);
+/* Same, fused with what follows it in the reference's graph: the slice/cat backward that puts the composite's
+ * d logit into column 0 (Renderer.cpp:179-183) and TCNNWPFunction::backward's input scaling
+ * (grad * loss_scale).to(fp16) (TCNNWP.cpp:213-216).  Emits the field MLP's dL/dout directly:
+ * d_field_out[p,0] = half(d_logit[p]*field_loss_scale), d_field_out[p,k] = half(d_mlp_in[p,k]*inv_loss_scale*field_loss_scale). */
+int f2b_shader_prep_bwd_f16(const void* d_mlp_in_f16 /* [P,32] */, const float* d_logit /* [P] */,
+                            const int* pts_idx_bounds, const int* emb_idx, int n_rays, float inv_loss_scale,
+                            float field_loss_scale, void* d_field_out_f16 /* [P,16] */, float* d_app_emb, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Composite — replaces the Renderer::Render tail (src/Renderer/Renderer.cpp:107-150,196-208),

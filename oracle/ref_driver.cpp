@@ -104,6 +104,18 @@ int main(int argc, char** argv) {
   dump("rays_o", rays_o); dump("rays_d", rays_d); dump("gt_colors", gt_colors); dump("emb_idx", emb_idx);
   dump("rays_d_normed", (rays_d / torch::linalg_norm(rays_d, 2, -1, true)).contiguous());
 
+  // ---- edge samples: the operator alone, with its RNG draws replayed next to it --------------------
+  {
+    torch::manual_seed(4242);
+    auto [edge_pts, edge_anchors] = sampler->GetEdgeSamples(8192);
+    dump("edge_pts", edge_pts); dump("edge_anchors", edge_anchors);
+    torch::manual_seed(4242);
+    int n_edges = sampler->pers_octree_->edge_pool_.size();
+    Tensor edge_idx = torch::randint(0, n_edges, {8192}, CUDAInt);                                 // PersSampler.cu:456
+    Tensor edge_coord = torch::rand({8192, 2}, CUDAFloat) * 2.f - 1.f;                             // :457
+    dump("edge_idx", edge_idx); dump("edge_coord", edge_coord);
+  }
+
   // ---- sampler, VALIDATE mode (noise == 1) --------------------------------------------------------
   gdp->iter_step_ = 1;
   gdp->ray_march_fineness_ = 1.f;
@@ -127,16 +139,6 @@ int main(int argc, char** argv) {
   // ---- TRAIN mode: seeded RNG, replayed once to expose the internal draws -------------------------
   gdp->mode_ = RunningMode::TRAIN;
   const int64_t seed = 777;
-  {
-    torch::manual_seed(seed);
-    Tensor noise = ((torch::rand({1024 + n_rays + 10}, CUDAFloat) - .5f) + 1.f).contiguous();   // PersSampler.cu:377
-    noise.mul_(gdp->ray_march_fineness_);
-    Tensor bg = torch::rand({n_rays, 3}, CUDAFloat);                                               // Renderer.cpp:73
-    int n_edges = sampler->pers_octree_->edge_pool_.size();
-    Tensor edge_idx = torch::randint(0, n_edges, {8192}, CUDAInt);                                 // PersSampler.cu:456
-    Tensor edge_coord = torch::rand({8192, 2}, CUDAFloat) * 2.f - 1.f;                             // :457
-    dump("train_noise", noise); dump("train_bg", bg); dump("train_edge_idx", edge_idx); dump("train_edge_coord", edge_coord);
-  }
   Tensor stats_w0 = sampler->pers_octree_->tree_weight_stats_.clone();
   {
     torch::manual_seed(seed);
@@ -169,6 +171,19 @@ int main(int argc, char** argv) {
     dump("grad_feat_pool_nz_idx", nz.to(torch::kInt32));
     dump("grad_feat_pool_nz_val", g.index({nz}));
     dump_scalar("backward_nan", gdp->backward_nan_ ? 1.f : 0.f);
+  }
+  {   // replay of the RNG draws Render made, in its order.  Every TCNNWP forward allocates its output with
+      // torch::rand (TCNNWP.cpp:143), so the early-stop MLP call sits between the background and the edge draws.
+    const int64_t n_all = renderer->sample_result_.pts.size(0);
+    torch::manual_seed(seed);
+    Tensor noise = ((torch::rand({1024 + n_rays + 10}, CUDAFloat) - .5f) + 1.f).contiguous();   // PersSampler.cu:377
+    noise.mul_(gdp->ray_march_fineness_);
+    Tensor bg = torch::rand({n_rays, 3}, CUDAFloat);                                               // Renderer.cpp:73
+    Tensor burn = torch::rand({(n_all + 127) / 128 * 128, 16}, torch::TensorOptions().dtype(torch::kFloat16).device(torch::kCUDA));
+    int n_edges = sampler->pers_octree_->edge_pool_.size();
+    Tensor edge_idx = torch::randint(0, n_edges, {8192}, CUDAInt);                                 // PersSampler.cu:456
+    Tensor edge_coord = torch::rand({8192, 2}, CUDAFloat) * 2.f - 1.f;                             // :457
+    dump("train_noise", noise); dump("train_bg", bg); dump("train_edge_idx", edge_idx); dump("train_edge_coord", edge_coord);
   }
 
   // ---- timing: Render + backward, CUDA events on the default stream ------------------------------

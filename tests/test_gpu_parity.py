@@ -267,6 +267,51 @@ def test_shader_prep_bwd(oracle):
     np.testing.assert_allclose(N(d2)[:, 1:], gf[:, 1:], rtol=1e-6)
 
 
+def test_rng_burn_matches_torch_rand():
+    """rng.burn_rand must leave the CUDA generator exactly where a real torch.rand / rand_like leaves it."""
+    from f2nerf_b200.rng import burn_mlp_output, burn_rand
+    for numel, dt in ((1, torch.float16), (255, torch.float32), (1024 * 16, torch.float16), (4_190_123 * 3, torch.float32),
+                      (1184 * 256 * 4 + 1, torch.float16), (33_554_432 + 16, torch.float16)):
+        torch.manual_seed(5)
+        torch.rand(numel, dtype=dt, device=DEV)
+        a = torch.rand(8, device=DEV)
+        torch.manual_seed(5)
+        burn_rand(numel, DEV)
+        b = torch.rand(8, device=DEV)
+        assert torch.equal(a, b), numel
+    torch.manual_seed(6)
+    torch.rand((128 * 3, 16), dtype=torch.float16, device=DEV)
+    a = torch.randint(0, 1000, (16,), device=DEV)
+    torch.manual_seed(6)
+    burn_mlp_output(257, DEV)                                     # 257 rows -> padded to 384
+    assert torch.equal(a, torch.randint(0, 1000, (16,), device=DEV))
+
+
+def test_shader_prep_bwd_fused_f16(oracle):
+    """The fused variant must equal  cast_f32_to_f16(d_scene_feat, field_scale)  of the two-step path, bit for bit."""
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(34)
+    n_emb = 17
+    lens = rng.integers(0, 150, 200).astype(np.int32); lens[0] = 0; lens[7] = 1
+    bounds = np.stack([np.cumsum(lens) - lens, np.cumsum(lens)], -1).astype(np.int32)
+    n = int(lens.sum())
+    g = (rng.standard_normal((n, 32)) * 3).astype(np.float16)
+    d_logit = (rng.standard_normal(n) * 1e-3).astype(np.float32)
+    ray_idx = rng.integers(0, n_emb, 200).astype(np.int32)
+    for s_scale, f_scale in ((128.0, 128.0), (64.0, 128.0)):
+        d_scene = torch.zeros((n, 16), device=DEV)
+        d_scene[:, 0] = T(d_logit)
+        d_app0 = torch.zeros((n_emb, 16), device=DEV)
+        ops.shader_prep_bwd(T(g), T(bounds), T(ray_idx), 1 / s_scale, d_scene, d_app0)
+        want = N(ops.cast_f32_to_f16(d_scene, f_scale))
+        out = torch.full((n + 5, 16), 9.0, dtype=torch.float16, device=DEV)
+        d_app1 = torch.zeros((n_emb, 16), device=DEV)
+        ops.shader_prep_bwd_f16(T(g), T(d_logit), T(bounds), T(ray_idx), 1 / s_scale, f_scale, out, d_app1)
+        np.testing.assert_array_equal(N(out)[:n].view(np.uint16), want.view(np.uint16))
+        assert (N(out)[n:] == 9.0).all()                           # rows past the rays' samples (edge points) untouched
+        assert_close(N(d_app1), N(d_app0).astype(np.float64), rtol=1e-4, atol_frac=1e-5, name="d_app_emb fused")
+
+
 # -------------------------------------------------------------------------------- composite ----
 def composite_inputs(scene, oracle, n_rays=300, seed=41):
     s = sample_points(scene, oracle, n_rays)

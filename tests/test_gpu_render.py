@@ -32,14 +32,18 @@ def test_render_train_step_matches_oracle(scene, oracle, n_rays, gs_progress):
     o, d, dn, cam = make_rays(scene, n_rays, seed=77)
     rays_o, rays_d, emb_idx = T(o), T(d), T(cam)
     seed = 321
-    torch.manual_seed(seed)                            # replay the internal draws (same order as Render)
-    noise = sampler.make_noise(n_rays, rays_o.device).clone()
-    bg = torch.rand((n_rays, 3), device="cuda")
-    e_idx = torch.randint(0, sampler.n_edges, (8192,), dtype=torch.int32, device="cuda")
-    e_coord = torch.rand((8192, 2), device="cuda") * 2. - 1.
     stats0 = N(sampler.tree_weight_stats_).copy()
     torch.manual_seed(seed)
     res = renderer.Render(rays_o, rays_d, None, emb_idx)
+    state = torch.cuda.get_rng_state()
+    torch.manual_seed(seed)                            # replay the internal draws, same order as Render ...
+    noise = sampler.make_noise(n_rays, rays_o.device).clone()
+    bg = torch.rand((n_rays, 3), device="cuda")
+    from f2nerf_b200.rng import burn_mlp_output        # ... incl. the reference's torch::rand MLP output (TCNNWP.cpp:143)
+    burn_mlp_output(renderer.sample_result_.pts.shape[0], rays_o.device)
+    e_idx = torch.randint(0, sampler.n_edges, (8192,), dtype=torch.int32, device="cuda")
+    e_coord = torch.rand((8192, 2), device="cuda") * 2. - 1.
+    torch.cuda.set_rng_state(state)
     gt = torch.rand((n_rays, 3), device="cuda", generator=torch.Generator("cuda").manual_seed(9))
     color_loss = torch.sqrt((res.colors - gt) ** 2 + 1e-4).mean()
     var_loss = torch.sqrt(CustomOps.WeightVar(res.weights, res.idx_start_end) + 1e-2).mean()
