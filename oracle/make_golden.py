@@ -36,8 +36,12 @@ def main():
             "train_noise", "train_bg", "train_edge_idx", "train_edge_coord", "train_pts", "train_dt", "train_t", "train_anchors",
             "train_bounds", "train_colors", "train_disparity", "train_depth", "train_weights", "train_idx_start_end",
             "train_first_oct_dis", "train_tree_nodes_after", "train_weight_stats_after", "train_alpha_stats_after",
-            "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb"]
+            "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb",
+            "edge_idx", "edge_coord", "edge_pts", "edge_anchors", "train_edge_feats"]
     data = {k: np.load(os.path.join(out, k + ".npy")) for k in keep}
+    for k in ("edge_idx", "edge_coord", "edge_pts", "edge_anchors"):         # 2048 of the 8192 draws are plenty
+        data[k] = np.ascontiguousarray(data[k][:2048])
+    data["train_edge_feats"] = np.ascontiguousarray(data["train_edge_feats"][:2048]).astype(np.float16)   # fp16 values
     # the level scales as the device computes them (MUFU.EX2): the oracle takes them as an input
     sys.path.insert(0, ROOT)
     from f2nerf_b200 import ops

@@ -60,9 +60,29 @@ def test_sampler_bit_exact_vs_reference(g, oracle, mode):
         np.testing.assert_array_equal(bits(got["first_oct_dis"]), bits(g["train_first_oct_dis"]))
 
 
-def test_edge_samples_feed_reference_edge_feats(g, oracle):
-    pts, idx = oracle.edge_samples(g["edge_pool"], g["pers_trans"], g["train_edge_idx"], g["train_edge_coord"])
-    assert np.isfinite(pts).all() and idx.min() >= 0 and idx.max() < scalars(g)["V"]
+def test_edge_samples_bit_exact_vs_reference(g, oracle):
+    """GetEdgeSamplesKernel (PersSampler.cu:436-452) on the reference's own seeded draws."""
+    pts, idx = oracle.edge_samples(g["edge_pool"], g["pers_trans"], g["edge_idx"], g["edge_coord"])
+    np.testing.assert_array_equal(idx, g["edge_anchors"])
+    np.testing.assert_array_equal(bits(pts), bits(g["edge_pts"]))
+
+
+def test_train_edge_feats_vs_reference(g, oracle):
+    """Renderer::Render's TV-loss branch: the replayed draws (incl. the torch::rand MLP-output buffer the reference
+    burns between background and edge draws, TCNNWP.cpp:143) must reproduce the edge features it returned."""
+    s = scalars(g)
+    n = g["train_edge_feats"].shape[0]
+    pts, idx = oracle.edge_samples(g["edge_pool"], g["pers_trans"], g["train_edge_idx"][:n], g["train_edge_coord"][:n])
+    gen = torch.Generator().manual_seed(1234)
+    table = (torch.rand((s["pool"], 2), generator=gen) * 2. - 1.).numpy().astype(np.float16)
+    local = ((s["pool"] // 16) >> 4) << 4
+    feat = oracle.hash_fwd(table, g["prim_pool"], g["bias_pool"], s["V"], local, g["level_scales"],
+                           np.ascontiguousarray(pts.reshape(-1, 3)), np.ascontiguousarray(idx.reshape(-1)), 1)
+    out, _ = oracle.mlp_fwd(feat, g["field_mlp_params"].astype(np.float16), 0)
+    ref = g["train_edge_feats"].astype(np.float32).reshape(-1, 16)
+    err = np.abs(out.astype(np.float32) - ref)
+    scale = np.abs(ref).max()
+    assert np.median(err) <= 2e-3 * scale and err.max() <= 0.03 * scale, (np.median(err), err.max(), scale)
 
 
 def test_field_and_shader_vs_tcnn(g, oracle):
