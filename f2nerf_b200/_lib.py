@@ -49,6 +49,7 @@ SIGNATURES = {
     "f2b_hash_fwd": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P],
     "f2b_hash_bwd": [_P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
     "f2b_mlp_fwd": [_P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_mlp_fwd_f32": [_P, _P, c_int, c_int, _P, _P, _P, _P],
     "f2b_mlp_bwd": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_v0": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_bwd_v0": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],

@@ -13,7 +13,9 @@ extern "C" int f2b_mlp_bwd_v0(const void*, const void*, const void*, const void*
 #ifdef F2B_HAVE_TC
 extern "C" int f2b_mlp_fwd_tc(const void*, const void*, int, int, void*, void*, void*);
 extern "C" int f2b_mlp_bwd_tc(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
+extern "C" int f2b_mlp_fwd_tc_f32(const void*, const void*, int, int, float*, void*, void*, void*);
 #endif
+extern "C" int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
 
 static int g_mlp_bwd_impl = -1;
 static int mlp_bwd_impl() {          // backward implementation follows F2B_MLP_BWD_IMPL, else the forward choice
@@ -59,6 +61,16 @@ extern "C" int f2b_mlp_fwd(const void* in_f16, const void* params_f16, int n_hid
   if (mlp_impl() == 1) return f2b_mlp_fwd_tc(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f16, hidden_save_f16, stream);
 #endif
   return f2b_mlp_fwd_v0(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f16, hidden_save_f16, stream);
+}
+extern "C" int f2b_mlp_fwd_f32(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                               float* out_f32, void* out_f16, void* hidden_save_f16, void* stream) {
+#ifdef F2B_HAVE_TC
+  if (mlp_impl() == 1) return f2b_mlp_fwd_tc_f32(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f32, out_f16, hidden_save_f16, stream);
+#endif
+  if (!out_f16) { f2b::set_error("f2b_mlp_fwd_f32: the CUDA-core twin needs the fp16 output buffer as well"); return F2B_EINVAL; }
+  const int rc = f2b_mlp_fwd_v0(in_f16, params_f16, n_hidden_matmuls, n_pts, out_f16, hidden_save_f16, stream);
+  if (rc != F2B_OK || !out_f32) return rc;
+  return f2b_cast_f16_to_f32(out_f16, out_f32, int64_t(n_pts) * 16, 1.f, stream);
 }
 extern "C" int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
                            const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,

@@ -11,8 +11,13 @@
 //     pull their accumulator row out of TMEM with tcgen05.ld (32x32b), apply ReLU, round to fp16 and
 //     write the next layer's operand row straight back to shared memory — activations never visit HBM
 //     except for the optional hidden_save the backward pass needs;
-//   * TMEM: 64 columns per CTA (the 16-column output accumulator reuses the hidden one), so up to
-//     8 CTAs share an SM and overlap one tile's global loads with another's MMA/epilogue.
+//   * global traffic is decoupled from the per-thread row ownership: the next tile's input is fetched with
+//     cp.async (16 B per thread, linear sweep of the contiguous 8 KB tile) into the second half of a double
+//     buffer while the current tile computes, and each finished activation tile is copied out to hidden_save
+//     by all threads as whole 128 B lines WHILE the tensor core is consuming the same tile for the next layer
+//     (r01 profile: per-row 16 B stores at 128 B stride + exposed load latency were ~50 % of the stall samples);
+//   * TMEM: 64 columns per CTA (the 16-column output accumulator reuses the hidden one); 3 (NH=1) or 5 (NH=0)
+//     CTAs share an SM (shared-memory bound) and overlap each other's MMA round trips.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -22,14 +27,16 @@ using namespace tc;
 constexpr int kTcTile = 128;
 constexpr int kTmemCols = 64;
 
+template <int NH>
 struct TcSmem {                         // offsets from a 1024-byte aligned base
-  static constexpr int A0 = 0;          // [128 x 32] f16, SW64   (8 KB)
-  static constexpr int A1 = 8192;       // [128 x 64] f16, SW128  (16 KB)
-  static constexpr int W0 = 24576;      // [64 x 32]  f16, SW64   (4 KB)
-  static constexpr int WH = 28672;      // [64 x 64]  f16, SW128  (8 KB)
-  static constexpr int WO = 36864;      // [16 x 64]  f16, SW128  (2 KB)
-  static constexpr int BAR = 38912;     // mbarrier (8 B) + tmem base (4 B)
-  static constexpr int BYTES = 38912 + 64 + 1024;   // + alignment slack
+  static constexpr int A0 = 0;          // 2 x [128 x 32] f16, SW64   (double-buffered input tile, 2 x 8 KB)
+  static constexpr int H0 = 16384;      // [128 x 64] f16, SW128  (16 KB)  layer-0 activations
+  static constexpr int H1 = 32768;      // [128 x 64] f16, SW128  (16 KB)  hidden-layer activations (NH only)
+  static constexpr int W0 = NH ? 49152 : 32768;   // [64 x 32]  f16, SW64   (4 KB)
+  static constexpr int WH = W0 + 4096;            // [64 x 64]  f16, SW128  (8 KB, NH only)
+  static constexpr int WO = WH + (NH ? 8192 : 0); // [16 x 64]  f16, SW128  (2 KB)
+  static constexpr int BAR = WO + 2048;           // mbarrier (8 B) + tmem base (4 B)
+  static constexpr int BYTES = BAR + 64 + 1024;   // + alignment slack
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -48,128 +55,144 @@ __device__ __forceinline__ void stage_weights(const __half* __restrict__ w, int 
   }
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Input tile (128 rows x 64 B, contiguous in global memory) -> swizzled K-major tile, fully coalesced:
+// the CTA's 128 threads sweep the 8 KB linearly, 16 B per thread and pass.
+__device__ __forceinline__ void prefetch_input(const __half* __restrict__ in, int tile, int n_pts, uint32_t a0_tile) {
+  const int rows = min(kTcTile, n_pts - tile * kTcTile);
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(in) + size_t(tile) * kTcTile * 64;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = threadIdx.x + kTcTile * j, r = c >> 2;
+    cp_async16(a0_tile + sw64_off(r, c & 3), src + (r < rows ? size_t(c) * 16 : 0), r < rows ? 16u : 0u);
+  }
+}
+
+// Activation tile (swizzled, 128 rows x 128 B) -> its contiguous 16 KB slot in the hidden_save array.  Runs
+// while the tensor core consumes the same tile: both only read it.
+__device__ __forceinline__ void copy_out_hidden(const unsigned char* h_tile, __half* __restrict__ dst_base, int tile, int n_pts) {
+  const int rows = min(kTcTile, n_pts - tile * kTcTile);
+  uint4* dst = reinterpret_cast<uint4*>(dst_base + size_t(tile) * kTcTile * 64);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = threadIdx.x + kTcTile * j, r = c >> 3;
+    if (r < rows) dst[c] = *reinterpret_cast<const uint4*>(h_tile + sw128_off(r, c & 7));
+  }
+}
+
+// accumulator row (64 fp32 in TMEM) -> ReLU -> fp16 -> my row of the next operand tile
+__device__ __forceinline__ void relu_epilogue(uint32_t tmem_row, unsigned char* h_tile, int row) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t r[16];
+    tmem_ld16(tmem_row + 16 * q, r);
+    tmem_ld_wait();
+    uint4 v0, v1;
+    v0.x = pack_half2(fmaxf(__uint_as_float(r[0]), 0.f), fmaxf(__uint_as_float(r[1]), 0.f));
+    v0.y = pack_half2(fmaxf(__uint_as_float(r[2]), 0.f), fmaxf(__uint_as_float(r[3]), 0.f));
+    v0.z = pack_half2(fmaxf(__uint_as_float(r[4]), 0.f), fmaxf(__uint_as_float(r[5]), 0.f));
+    v0.w = pack_half2(fmaxf(__uint_as_float(r[6]), 0.f), fmaxf(__uint_as_float(r[7]), 0.f));
+    v1.x = pack_half2(fmaxf(__uint_as_float(r[8]), 0.f), fmaxf(__uint_as_float(r[9]), 0.f));
+    v1.y = pack_half2(fmaxf(__uint_as_float(r[10]), 0.f), fmaxf(__uint_as_float(r[11]), 0.f));
+    v1.z = pack_half2(fmaxf(__uint_as_float(r[12]), 0.f), fmaxf(__uint_as_float(r[13]), 0.f));
+    v1.w = pack_half2(fmaxf(__uint_as_float(r[14]), 0.f), fmaxf(__uint_as_float(r[15]), 0.f));
+    *reinterpret_cast<uint4*>(h_tile + sw128_off(row, 2 * q)) = v0;
+    *reinterpret_cast<uint4*>(h_tile + sw128_off(row, 2 * q + 1)) = v1;
+  }
+}
+
 template <int NH>
 __global__ void __launch_bounds__(kTcTile)
 mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ params, int n_pts,
-                  __half* __restrict__ out, __half* __restrict__ hidden_save) {
+                  __half* __restrict__ out, float* __restrict__ out_f32, __half* __restrict__ hidden_save) {
+  using S = TcSmem<NH>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + TcSmem::BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TcSmem::BAR + 8);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_pts + kTcTile - 1) / kTcTile;
+  const uint32_t a0 = smem_u32(sm + S::A0);
 
-  stage_weights<32>(params, 64, sm + TcSmem::W0);
-  if (NH) stage_weights<64>(params + 64 * 32, 64, sm + TcSmem::WH);
-  stage_weights<64>(params + 64 * 32 + NH * 64 * 64, 16, sm + TcSmem::WO);
+  int tile = blockIdx.x;
+  if (tile < n_tiles) prefetch_input(in, tile, n_pts, a0);       // overlaps the weight staging / TMEM allocation
+  cp_async_commit();
+  stage_weights<32>(params, 64, sm + S::W0);
+  if (NH) stage_weights<64>(params + 64 * 32, 64, sm + S::WH);
+  stage_weights<64>(params + 64 * 32 + NH * 64 * 64, 16, sm + S::WO);
   if (tid == 0) mbar_init(mbar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_row = tmem + (uint32_t(warp * 32) << 16);   // this warp's 32 TMEM lanes
 
-  const uint32_t a0 = smem_u32(sm + TcSmem::A0), a1 = smem_u32(sm + TcSmem::A1);
-  const uint32_t w0 = smem_u32(sm + TcSmem::W0), wh = smem_u32(sm + TcSmem::WH), wo = smem_u32(sm + TcSmem::WO);
+  const uint32_t h0 = smem_u32(sm + S::H0), h1 = smem_u32(sm + S::H1);
+  const uint32_t w0 = smem_u32(sm + S::W0), wh = smem_u32(sm + S::WH), wo = smem_u32(sm + S::WO);
   constexpr uint32_t idesc64 = idesc_f16_f32(128, 64), idesc16 = idesc_f16_f32(128, 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, buf = 0;
 
-  const int n_tiles = (n_pts + kTcTile - 1) / kTcTile;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
     const int p = tile * kTcTile + tid;
     const bool valid = p < n_pts;
-    // ---- stage the input row (64 B) into A0 -------------------------------------------------
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(in + size_t(p) * 32);
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const uint4 v = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sm + TcSmem::A0 + sw64_off(tid, c)) = v;
-      }
-    }
+    // ---- input: tile i has been in flight since the previous iteration; start tile i+1 now ---------
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) prefetch_input(in, next, n_pts, a0 + (buf ^ 1) * 8192);
+    cp_async_commit();
+    cp_async_wait<1>();                                          // everything but the newest group has landed
     fence_async_smem();
+    fence_before_sync();                                         // (the previous tile's TMEM reads are done)
     __syncthreads();
     // ---- layer 0: D[128x64] = A0[128x32] . W0^T ------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
+      const uint32_t a = a0 + buf * 8192;
 #pragma unroll
       for (int k = 0; k < 2; k++)
-        mma_f16(tmem, kmajor_desc(a0 + 32 * k, 64), kmajor_desc(w0 + 32 * k, 64), idesc64, k);
+        mma_f16(tmem, kmajor_desc(a + 32 * k, 64), kmajor_desc(w0 + 32 * k, 64), idesc64, k);
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    // epilogue: ReLU, fp16, write my row of A1 (and the hidden save)
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      uint32_t r[16];
-      tmem_ld16(tmem_row + 16 * q, r);
-      tmem_ld_wait();
-      uint4 v0, v1;
-      v0.x = pack_half2(fmaxf(__uint_as_float(r[0]), 0.f), fmaxf(__uint_as_float(r[1]), 0.f));
-      v0.y = pack_half2(fmaxf(__uint_as_float(r[2]), 0.f), fmaxf(__uint_as_float(r[3]), 0.f));
-      v0.z = pack_half2(fmaxf(__uint_as_float(r[4]), 0.f), fmaxf(__uint_as_float(r[5]), 0.f));
-      v0.w = pack_half2(fmaxf(__uint_as_float(r[6]), 0.f), fmaxf(__uint_as_float(r[7]), 0.f));
-      v1.x = pack_half2(fmaxf(__uint_as_float(r[8]), 0.f), fmaxf(__uint_as_float(r[9]), 0.f));
-      v1.y = pack_half2(fmaxf(__uint_as_float(r[10]), 0.f), fmaxf(__uint_as_float(r[11]), 0.f));
-      v1.z = pack_half2(fmaxf(__uint_as_float(r[12]), 0.f), fmaxf(__uint_as_float(r[13]), 0.f));
-      v1.w = pack_half2(fmaxf(__uint_as_float(r[14]), 0.f), fmaxf(__uint_as_float(r[15]), 0.f));
-      *reinterpret_cast<uint4*>(sm + TcSmem::A1 + sw128_off(tid, 2 * q)) = v0;
-      *reinterpret_cast<uint4*>(sm + TcSmem::A1 + sw128_off(tid, 2 * q + 1)) = v1;
-      if (hidden_save && valid) {
-        uint4* dst = reinterpret_cast<uint4*>(hidden_save + size_t(p) * 64) + 2 * q;
-        dst[0] = v0; dst[1] = v1;
-      }
-    }
+    relu_epilogue(tmem_row, sm + S::H0, tid);
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
     if (NH) {
-      // ---- hidden layer: D[128x64] = A1[128x64] . Wh^T, result back into A1 -------------------------
+      // ---- hidden layer: D[128x64] = H0[128x64] . Wh^T ---------------------------------------------
       if (tid == 0) {
         fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          mma_f16(tmem, kmajor_desc(a1 + 32 * k, 128), kmajor_desc(wh + 32 * k, 128), idesc64, k);
+          mma_f16(tmem, kmajor_desc(h0 + 32 * k, 128), kmajor_desc(wh + 32 * k, 128), idesc64, k);
         mma_commit(mbar);
       }
+      if (hidden_save) copy_out_hidden(sm + S::H0, hidden_save, tile, n_pts);        // while the MMA runs
       mbar_wait(mbar, phase); phase ^= 1;
       fence_after_sync();
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint32_t r[16];
-        tmem_ld16(tmem_row + 16 * q, r);
-        tmem_ld_wait();
-        uint4 v0, v1;
-        v0.x = pack_half2(fmaxf(__uint_as_float(r[0]), 0.f), fmaxf(__uint_as_float(r[1]), 0.f));
-        v0.y = pack_half2(fmaxf(__uint_as_float(r[2]), 0.f), fmaxf(__uint_as_float(r[3]), 0.f));
-        v0.z = pack_half2(fmaxf(__uint_as_float(r[4]), 0.f), fmaxf(__uint_as_float(r[5]), 0.f));
-        v0.w = pack_half2(fmaxf(__uint_as_float(r[6]), 0.f), fmaxf(__uint_as_float(r[7]), 0.f));
-        v1.x = pack_half2(fmaxf(__uint_as_float(r[8]), 0.f), fmaxf(__uint_as_float(r[9]), 0.f));
-        v1.y = pack_half2(fmaxf(__uint_as_float(r[10]), 0.f), fmaxf(__uint_as_float(r[11]), 0.f));
-        v1.z = pack_half2(fmaxf(__uint_as_float(r[12]), 0.f), fmaxf(__uint_as_float(r[13]), 0.f));
-        v1.w = pack_half2(fmaxf(__uint_as_float(r[14]), 0.f), fmaxf(__uint_as_float(r[15]), 0.f));
-        // the MMA that read A1 has completed (mbarrier), so the row can be overwritten in place
-        *reinterpret_cast<uint4*>(sm + TcSmem::A1 + sw128_off(tid, 2 * q)) = v0;
-        *reinterpret_cast<uint4*>(sm + TcSmem::A1 + sw128_off(tid, 2 * q + 1)) = v1;
-        if (hidden_save && valid) {
-          uint4* dst = reinterpret_cast<uint4*>(hidden_save + size_t(n_pts) * 64 + size_t(p) * 64) + 2 * q;
-          dst[0] = v0; dst[1] = v1;
-        }
-      }
+      relu_epilogue(tmem_row, sm + S::H1, tid);
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
     }
-    // ---- output layer: D[128x16] = A1[128x64] . Wout^T (linear) ------------------------------------
+    // ---- output layer: D[128x16] = H_last[128x64] . Wout^T (linear) ----------------------------------
     if (tid == 0) {
       fence_after_sync();
+      const uint32_t hl = NH ? h1 : h0;
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        mma_f16(tmem, kmajor_desc(a1 + 32 * k, 128), kmajor_desc(wo + 32 * k, 128), idesc16, k);
+        mma_f16(tmem, kmajor_desc(hl + 32 * k, 128), kmajor_desc(wo + 32 * k, 128), idesc16, k);
       mma_commit(mbar);
     }
+    if (hidden_save) copy_out_hidden(sm + (NH ? S::H1 : S::H0), hidden_save + size_t(NH) * n_pts * 64, tile, n_pts);
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
     {
@@ -182,13 +205,26 @@ mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ para
         v0.z = pack_half2(__uint_as_float(r[4]), __uint_as_float(r[5]));   v0.w = pack_half2(__uint_as_float(r[6]), __uint_as_float(r[7]));
         v1.x = pack_half2(__uint_as_float(r[8]), __uint_as_float(r[9]));   v1.y = pack_half2(__uint_as_float(r[10]), __uint_as_float(r[11]));
         v1.z = pack_half2(__uint_as_float(r[12]), __uint_as_float(r[13])); v1.w = pack_half2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-        uint4* dst = reinterpret_cast<uint4*>(out + size_t(p) * 16);
-        dst[0] = v0; dst[1] = v1;
+        if (out) {
+          uint4* dst = reinterpret_cast<uint4*>(out + size_t(p) * 16);
+          dst[0] = v0; dst[1] = v1;
+        }
+        if (out_f32) {                                           // the fp16-rounded values, widened (TCNNWP.cpp:112)
+          const __half2* h = reinterpret_cast<const __half2*>(&v0);
+          const __half2* g = reinterpret_cast<const __half2*>(&v1);
+          float4* dst = reinterpret_cast<float4*>(out_f32 + size_t(p) * 16);
+          const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+          const float2 e = __half22float2(g[0]), f = __half22float2(g[1]), u = __half22float2(g[2]), w = __half22float2(g[3]);
+          dst[0] = make_float4(a.x, a.y, b.x, b.y); dst[1] = make_float4(c.x, c.y, d.x, d.y);
+          dst[2] = make_float4(e.x, e.y, f.x, f.y); dst[3] = make_float4(u.x, u.y, w.x, w.y);
+        }
       }
     }
-    fence_before_sync();
-    __syncthreads();          // TMEM columns and A0/A1 are free for the next tile
+    // the next iteration's barrier orders these TMEM reads before the next tile's first MMA
   }
+  cp_async_wait<0>();
+  fence_before_sync();
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -196,23 +232,37 @@ mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ para
 
 using namespace f2b;
 
+template <int NH>
+static void launch_fwd(const void* in_f16, const void* params_f16, int n_pts, void* out_f16, float* out_f32,
+                       void* hidden_save_f16, void* stream) {
+  int sms = 148;
+  f2b_device_info(&sms, nullptr);
+  const int per_sm = NH ? 3 : 5;                                  // shared-memory bound (63 KB / 39 KB per CTA)
+  const int n_tiles = div_up(n_pts, kTcTile);
+  const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+  cudaFuncSetAttribute(mlp_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<NH>::BYTES);
+  mlp_fwd_tc_kernel<NH><<<grid, kTcTile, TcSmem<NH>::BYTES, as_stream(stream)>>>(
+      (const __half*)in_f16, (const __half*)params_f16, n_pts, (__half*)out_f16, out_f32, (__half*)hidden_save_f16);
+}
+
 extern "C" int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
                               void* out_f16, void* hidden_save_f16, void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(in_f16 && params_f16 && out_f16, "f2b_mlp_fwd: null pointer");
   F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_fwd: n_hidden_matmuls must be 0 or 1");
-  int sms = 148;
-  f2b_device_info(&sms, nullptr);
-  const int n_tiles = div_up(n_pts, kTcTile);
-  const int grid = n_tiles < sms * 5 ? n_tiles : sms * 5;
-  if (n_hidden_matmuls == 0) {
-    cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES);
-    mlp_fwd_tc_kernel<0><<<grid, kTcTile, TcSmem::BYTES, as_stream(stream)>>>((const __half*)in_f16, (const __half*)params_f16,
-                                                                              n_pts, (__half*)out_f16, (__half*)hidden_save_f16);
-  } else {
-    cudaFuncSetAttribute(mlp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES);
-    mlp_fwd_tc_kernel<1><<<grid, kTcTile, TcSmem::BYTES, as_stream(stream)>>>((const __half*)in_f16, (const __half*)params_f16,
-                                                                              n_pts, (__half*)out_f16, (__half*)hidden_save_f16);
-  }
+  if (n_hidden_matmuls == 0) launch_fwd<0>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, stream);
+  else launch_fwd<1>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, stream);
   return check_launch("f2b_mlp_fwd(tcgen05)");
+}
+
+// Same network, output widened to fp32 in the epilogue (what TCNNWP::Query hands back, TCNNWP.cpp:112):
+// out_f32 [P,16] and/or out_f16 [P,16] (either may be NULL, not both).
+extern "C" int f2b_mlp_fwd_tc_f32(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                               float* out_f32, void* out_f16, void* hidden_save_f16, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(in_f16 && params_f16 && (out_f32 || out_f16), "f2b_mlp_fwd_f32: null pointer");
+  F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_fwd_f32: n_hidden_matmuls must be 0 or 1");
+  if (n_hidden_matmuls == 0) launch_fwd<0>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, stream);
+  else launch_fwd<1>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, stream);
+  return check_launch("f2b_mlp_fwd_f32(tcgen05)");
 }

@@ -19,18 +19,21 @@ using namespace tc;
 
 constexpr int kBT = 128;   // tile rows
 
+// Shared memory: resident weights, then TWO stages of per-tile operands (double-buffered cp.async prefetch).
+// The activation gradients overwrite the activations they mask in place (dH1 over H1, dH0 over H0): every MMA
+// that still needs the forward activation as an operand is issued in the step BEFORE the overwrite.
 template <int NH>
 struct BwdSmem {
-  static constexpr int W0 = 0;                       // [64 x 32]  SW64   4 KB   (B operand, MN-major, K = out row)
-  static constexpr int WH = 4096;                    // [64 x 64]  SW128  8 KB
-  static constexpr int WO = 12288;                   // [16 x 64]  SW128  2 KB
-  static constexpr int DO = 14336;                   // [128 x 16] SW32   4 KB
-  static constexpr int X = 18432;                    // [128 x 32] SW64   8 KB
-  static constexpr int H0 = 26624;                   // [128 x 64] SW128 16 KB
-  static constexpr int DH0 = 43008;                  // [128 x 64] SW128 16 KB
-  static constexpr int H1 = 59392;                   // NH only
-  static constexpr int DH1 = 75776;                  // NH only
-  static constexpr int BAR = NH ? 92160 : 59392;
+  static constexpr int W0 = 0;                              // [64 x 32]  SW64   4 KB   (B operand, MN-major, K = out row)
+  static constexpr int WH = 4096;                           // [64 x 64]  SW128  8 KB   (NH only)
+  static constexpr int WO = NH ? 12288 : 4096;              // [16 x 64]  SW128  2 KB
+  static constexpr int STAGE0 = WO + 2048;
+  static constexpr int DO = 0;                              // stage-relative: [128 x 16] SW32   4 KB
+  static constexpr int X = 4096;                            //                 [128 x 32] SW64   8 KB
+  static constexpr int H0 = 12288;                          //                 [128 x 64] SW128 16 KB (becomes dH0)
+  static constexpr int H1 = 28672;                          //                 [128 x 64] SW128 16 KB (becomes dH1; NH only)
+  static constexpr int STAGE_BYTES = NH ? 45056 : 28672;
+  static constexpr int BAR = STAGE0 + 2 * STAGE_BYTES;
   static constexpr int BYTES = BAR + 64 + 1024;
   static constexpr int TMEM_COLS = NH ? 256 : 128;
   static constexpr int C_ACT = 0, C_GW0 = 64, C_GWO = 96, C_GWH = 128;
@@ -53,6 +56,44 @@ __device__ __forceinline__ void stage_w(const __half* __restrict__ w, int rows, 
   for (int i = threadIdx.x; i < rows * chunks; i += blockDim.x) {
     const int r = i / chunks, c = i % chunks;
     *reinterpret_cast<uint4*>(dst + (K == 64 ? sw128_off(r, c) : sw64_off(r, c))) = *reinterpret_cast<const uint4*>(w + r * K + c * 8);
+  }
+}
+
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// One tile's operand rows (dOut 32 B, x 64 B, h0 128 B, h1 128 B per sample; each a contiguous block in global
+// memory) -> swizzled tiles of one stage, 16 B per thread and pass, linear sweep = full 128 B lines.
+template <int NH>
+__device__ __forceinline__ void prefetch_tile(const __half* __restrict__ dout, const __half* __restrict__ in,
+                                              const __half* __restrict__ hidden, const __half* __restrict__ hid_last,
+                                              int tile, int n_pts, uint32_t stage) {
+  using S = BwdSmem<NH>;
+  const int rows = min(kBT, n_pts - tile * kBT);
+  const size_t t0 = size_t(tile) * kBT;
+  const unsigned char* s_do = reinterpret_cast<const unsigned char*>(dout + t0 * 16);
+  const unsigned char* s_x = reinterpret_cast<const unsigned char*>(in + t0 * 32);
+  const unsigned char* s_h0 = reinterpret_cast<const unsigned char*>(hidden + t0 * 64);
+  const unsigned char* s_h1 = reinterpret_cast<const unsigned char*>(hid_last + t0 * 64);
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int c = threadIdx.x + kBT * j, r = c >> 1;
+    const bool ok = r < rows;
+    cp16(stage + S::DO + sw32_off(r, c & 1), s_do + (ok ? size_t(c) * 16 : 0), ok ? 16u : 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = threadIdx.x + kBT * j, r = c >> 2;
+    const bool ok = r < rows;
+    cp16(stage + S::X + sw64_off(r, c & 3), s_x + (ok ? size_t(c) * 16 : 0), ok ? 16u : 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = threadIdx.x + kBT * j, r = c >> 3;
+    const bool ok = r < rows;
+    cp16(stage + S::H0 + sw128_off(r, c & 7), s_h0 + (ok ? size_t(c) * 16 : 0), ok ? 16u : 0u);
+    if (NH) cp16(stage + S::H1 + sw128_off(r, c & 7), s_h1 + (ok ? size_t(c) * 16 : 0), ok ? 16u : 0u);
   }
 }
 
@@ -88,100 +129,90 @@ mlp_bwd_tc_kernel(const __half* __restrict__ dout, const __half* __restrict__ in
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (n_pts + kBT - 1) / kBT;
+  const __half* hid_last = hidden + size_t(NH) * n_pts * 64;
+  const uint32_t stage0 = smem_u32(sm + S::STAGE0);
 
+  int tile = blockIdx.x;
+  if (tile < n_tiles) prefetch_tile<NH>(dout, in, hidden, hid_last, tile, n_pts, stage0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   stage_w<32>(params, 64, sm + S::W0);
   if (NH) stage_w<64>(params + 64 * 32, 64, sm + S::WH);
   stage_w<64>(params + 64 * 32 + NH * 64 * 64, 16, sm + S::WO);
   if (tid == 0) mbar_init(mbar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, S::TMEM_COLS);
-  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_row = tmem + (uint32_t(warp * 32) << 16);
   const uint32_t s_w0 = smem_u32(sm + S::W0), s_wh = smem_u32(sm + S::WH), s_wo = smem_u32(sm + S::WO);
-  const uint32_t s_do = smem_u32(sm + S::DO), s_x = smem_u32(sm + S::X), s_h0 = smem_u32(sm + S::H0);
-  const uint32_t s_dh0 = smem_u32(sm + S::DH0), s_h1 = smem_u32(sm + S::H1), s_dh1 = smem_u32(sm + S::DH1);
-  unsigned char* const h_last = sm + (NH ? S::H1 : S::H0);
-  unsigned char* const dh_last = sm + (NH ? S::DH1 : S::DH0);
-  const uint32_t s_hl = NH ? s_h1 : s_h0, s_dhl = NH ? s_dh1 : s_dh0;
   // instruction descriptors
   constexpr uint32_t id_act64 = idesc_f16_f32(128, 64, 0, 1);     // A K-major, B MN-major
   constexpr uint32_t id_act32 = idesc_f16_f32(128, 32, 0, 1);
   constexpr uint32_t id_gw16 = idesc_f16_f32(64, 16, 1, 1);       // both MN-major
   constexpr uint32_t id_gw32 = idesc_f16_f32(64, 32, 1, 1);
   constexpr uint32_t id_gw64 = idesc_f16_f32(64, 64, 1, 1);
-  uint32_t phase = 0, first = 1;
+  uint32_t phase = 0, first = 1, buf = 0;
 
-  const int n_tiles = (n_pts + kBT - 1) / kBT;
-  const __half* hid_last = hidden + size_t(NH) * n_pts * 64;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
     const int p = tile * kBT + tid;
     const bool valid = p < n_pts;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    {   // stage this sample's rows: dOut (32 B), x (64 B), h0 (128 B), h1 (128 B)
-      const uint4* s = reinterpret_cast<const uint4*>(dout + size_t(p) * 16);
-#pragma unroll
-      for (int c = 0; c < 2; c++) *reinterpret_cast<uint4*>(sm + S::DO + sw32_off(tid, c)) = valid ? __ldg(s + c) : z;
-      s = reinterpret_cast<const uint4*>(in + size_t(p) * 32);
-#pragma unroll
-      for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(sm + S::X + sw64_off(tid, c)) = valid ? __ldg(s + c) : z;
-      s = reinterpret_cast<const uint4*>(hidden + size_t(p) * 64);
-#pragma unroll
-      for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sm + S::H0 + sw128_off(tid, c)) = valid ? __ldg(s + c) : z;
-      if (NH) {
-        s = reinterpret_cast<const uint4*>(hid_last + size_t(p) * 64);
-#pragma unroll
-        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sm + S::H1 + sw128_off(tid, c)) = valid ? __ldg(s + c) : z;
-      }
-    }
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) prefetch_tile<NH>(dout, in, hidden, hid_last, next, n_pts, stage0 + (buf ^ 1) * S::STAGE_BYTES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");         // this tile's operands have landed
     fence_async_smem();
+    fence_before_sync();
     __syncthreads();
-    // ---- A: dH_last = dOut . Wout  (K = 16) -----------------------------------------------------
+    unsigned char* const st = sm + S::STAGE0 + buf * S::STAGE_BYTES;
+    const uint32_t sb = stage0 + buf * S::STAGE_BYTES;
+    const uint32_t s_do = sb + S::DO, s_x = sb + S::X, s_h0 = sb + S::H0, s_h1 = sb + S::H1;
+    const uint32_t s_hl = NH ? s_h1 : s_h0;
+    const uint32_t acc = (first ^ 1);
+    // ---- A: dH_last = dOut . Wout  (K = 16) ; dWout^T += H_last^T . dOut (needs H_last before it is overwritten)
     if (tid == 0) {
       fence_after_sync();
       mma_f16(tmem + S::C_ACT, kmajor_desc(s_do, 32), mnmajor_desc(s_wo, 128, 0), id_act64, 0);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        mma_f16(tmem + S::C_GWO, mnmajor_desc(s_hl, 128, k), mnmajor_desc(s_do, 32, k), id_gw16, (k > 0) | acc);
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
-    relu_bwd_epilogue(tmem_row + S::C_ACT, h_last, dh_last, tid);
+    relu_bwd_epilogue(tmem_row + S::C_ACT, st + (NH ? S::H1 : S::H0), st + (NH ? S::H1 : S::H0), tid);   // in place
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
     if (NH) {
-      // ---- B: dH0 = dH1 . Wh ; dWout^T += H1^T . dOut ; dWh += dH1^T . H0 -------------------------
+      // ---- B: dH0 = dH1 . Wh ; dWh += dH1^T . H0 (H0 still the forward activation) ---------------------
       if (tid == 0) {
         fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          mma_f16(tmem + S::C_ACT, kmajor_desc(s_dh1 + 32 * k, 128), mnmajor_desc(s_wh, 128, k), id_act64, k);
+          mma_f16(tmem + S::C_ACT, kmajor_desc(s_h1 + 32 * k, 128), mnmajor_desc(s_wh, 128, k), id_act64, k);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          mma_f16(tmem + S::C_GWO, mnmajor_desc(s_h1, 128, k), mnmajor_desc(s_do, 32, k), id_gw16, (k > 0) | (first ^ 1));
-          mma_f16(tmem + S::C_GWH, mnmajor_desc(s_dh1, 128, k), mnmajor_desc(s_h0, 128, k), id_gw64, (k > 0) | (first ^ 1));
-        }
+        for (int k = 0; k < 8; k++)
+          mma_f16(tmem + S::C_GWH, mnmajor_desc(s_h1, 128, k), mnmajor_desc(s_h0, 128, k), id_gw64, (k > 0) | acc);
         mma_commit(mbar);
       }
       mbar_wait(mbar, phase); phase ^= 1;
       fence_after_sync();
-      relu_bwd_epilogue(tmem_row + S::C_ACT, sm + S::H0, sm + S::DH0, tid);
+      relu_bwd_epilogue(tmem_row + S::C_ACT, st + S::H0, st + S::H0, tid);                                  // in place
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
     }
-    // ---- C: dIn = dH0 . W0 ; dW0 += dH0^T . X ; (NH == 0: dWout^T += H0^T . dOut) ---------------------
+    // ---- C: dIn = dH0 . W0 ; dW0 += dH0^T . X -----------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        mma_f16(tmem + S::C_ACT, kmajor_desc(s_dh0 + 32 * k, 128), mnmajor_desc(s_w0, 64, k), id_act32, k);
+        mma_f16(tmem + S::C_ACT, kmajor_desc(s_h0 + 32 * k, 128), mnmajor_desc(s_w0, 64, k), id_act32, k);
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        mma_f16(tmem + S::C_GW0, mnmajor_desc(s_dh0, 128, k), mnmajor_desc(s_x, 64, k), id_gw32, (k > 0) | (first ^ 1));
-        if (!NH) mma_f16(tmem + S::C_GWO, mnmajor_desc(s_hl, 128, k), mnmajor_desc(s_do, 32, k), id_gw16, (k > 0) | (first ^ 1));
-      }
+      for (int k = 0; k < 8; k++)
+        mma_f16(tmem + S::C_GW0, mnmajor_desc(s_h0, 128, k), mnmajor_desc(s_x, 64, k), id_gw32, (k > 0) | acc);
       mma_commit(mbar);
     }
     first = 0;
@@ -203,10 +234,11 @@ mlp_bwd_tc_kernel(const __half* __restrict__ dout, const __half* __restrict__ in
         }
       }
     }
-    fence_before_sync();
-    __syncthreads();
-    (void)s_dhl;
+    // the next iteration's barrier orders these TMEM reads before the next tile's first MMA
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  fence_before_sync();
+  __syncthreads();
   // ---- flush the weight-gradient accumulators (M = 64 layout: warp w, lanes 0..15 hold rows 16w..16w+15) ----
   if (!first) {
     fence_after_sync();

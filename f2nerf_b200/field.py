@@ -197,8 +197,8 @@ def field_forward(field, table16, params16, points, anchors, anchor_stride, save
 
 def field_forward_from_features(field, params16, feat16, save):
     """MLP on already-encoded features (rows re-used from the early-stop pass): -> (out fp32 [n,16], hidden)."""
-    out16, hidden = ops.mlp_fwd(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save)
-    return ops.cast_f16_to_f32(out16), hidden
+    out32, _, hidden = ops.mlp_fwd_f32(feat16, params16, field.mlp_.n_hidden_matmuls, save_hidden=save)
+    return out32, hidden
 
 
 def field_backward(field, params16, points, anchors, anchor_stride, feat16, hidden, d_out_f32, d_out_f16=None, segments=None):

@@ -137,6 +137,17 @@ def mlp_fwd(x_f16, params_f16, n_hidden_matmuls, save_hidden=False, impl=None):
     return out, hidden
 
 
+def mlp_fwd_f32(x_f16, params_f16, n_hidden_matmuls, save_hidden=False, want_f16=False):
+    """MLP forward returning fp32 [n,16] (fp16-rounded values) straight from the epilogue: -> (out32, out16|None, hidden)."""
+    from . import _lib
+    n = x_f16.shape[0]
+    out32 = dev_empty((n, 16), F32, x_f16)
+    out16 = dev_empty((n, 16), F16, x_f16) if (want_f16 or _lib.lib.f2b_get_mlp_impl() != 1) else None
+    hidden = dev_empty((n_hidden_matmuls + 1, n, 64), F16, x_f16) if save_hidden else None
+    call("f2b_mlp_fwd_f32", x_f16, params_f16, int(n_hidden_matmuls), n, out32, out16, hidden, stream())
+    return out32, out16, hidden
+
+
 def mlp_bwd(dout_f16, x_f16, hidden, params_f16, n_hidden_matmuls, need_din=True, impl=None):
     n = x_f16.shape[0]
     din = dev_empty((n, 32), F16, x_f16) if need_din else None

@@ -126,6 +126,11 @@ int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_volumes, in
  * hidden_save: nullable, [(n_hidden_matmuls+1), P, 64] fp16 forward activations for backward. */
 int f2b_mlp_fwd(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
                 void* out_f16, void* hidden_save_f16, void* stream);
+/* Same network with the output widened to fp32 in the epilogue — what TCNNWP::Query returns
+ * (`feat...to(torch::kFloat32)`, TCNNWP.cpp:112).  out_f32 [P,16] and/or out_f16 [P,16]; with the tcgen05
+ * implementation either may be NULL (not both), the CUDA-core twin needs out_f16. */
+int f2b_mlp_fwd_f32(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
+                    float* out_f32, void* out_f16, void* hidden_save_f16, void* stream);
 /* Backward: dL/dout [P,16] fp16 (already multiplied by loss_scale) -> dL/din [P,32] fp16 (nullable),
  * dL/dparams fp32 (same layout as params, accumulated in fp32; caller zeroes), both still scaled. */
 int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,

@@ -6,7 +6,7 @@ echo "== gpu: $(nvidia-smi -L) / nproc $(nproc) / impl $IMPL"
 F2B_MLP_IMPL=$IMPL timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_ref_parity.py -p no:cacheprovider -k "not tc and not fused" > gpurun_out/pytest_gpu.log 2>&1
 tail -n 40 gpurun_out/pytest_gpu.log
 # tensor-core kernels in their own processes (a faulting kernel must not poison the other tests)
-for K in "tc-0" "tc-1" "fused"; do
+for K in "tc-0" "tc-1" "fused" "tiles"; do
   timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "$K" > gpurun_out/pytest_$K.log 2>&1
   echo "--- -k $K"; tail -n 25 gpurun_out/pytest_$K.log | cut -c1-250
 done

@@ -195,6 +195,36 @@ def test_mlp_fwd_bwd(oracle, nh, impl):
     assert_close(N(dp), rdp, rtol=2e-3, atol_frac=2e-3, name="mlp dparams")
 
 
+@pytest.mark.parametrize("nh", [0, 1])
+def test_mlp_tc_tiles_and_f32_output(oracle, nh):
+    """Persistent-tile path of the tcgen05 forward: sizes below / across / far beyond one tile per CTA (double-buffered
+    cp.async input, coalesced hidden copy-out), tc == CUDA-core twin within fp16 noise, fp32 output == widened fp16."""
+    from f2nerf_b200 import ops
+    rng = np.random.default_rng(77 + nh)
+    params = T((oracle.mlp_init(32, nh) * 2).astype(np.float16))
+    for n in (1, 127, 128, 129, 5000, 148 * 5 * 128 * 2 + 333):
+        x = T((rng.standard_normal((n, 32)) * 0.5).astype(np.float16))
+        out, hid = ops.mlp_fwd(x, params, nh, save_hidden=True, impl="tc")
+        out0, hid0 = ops.mlp_fwd(x, params, nh, save_hidden=True, impl="v0")
+        # fp32 accumulation order differs (tensor core vs serial): fp16 roundings may flip on cancellation-small values
+        assert_close(N(hid)[0].astype(np.float32), N(hid0)[0].astype(np.float32), rtol=2e-3, atol_frac=1e-3, name=f"hidden n={n}")
+        assert_close(N(out).astype(np.float32), N(out0).astype(np.float32), rtol=4e-3, atol_frac=2e-3, name=f"tc vs v0 n={n}")
+        out32, out16, hid2 = ops.mlp_fwd_f32(x, params, nh, save_hidden=True, want_f16=True)
+        np.testing.assert_array_equal(N(out16).view(np.uint16), N(out).view(np.uint16))
+        np.testing.assert_array_equal(N(out32), N(out).astype(np.float32))
+        np.testing.assert_array_equal(N(hid2).view(np.uint16), N(hid).view(np.uint16))
+        out32b, none16, _ = ops.mlp_fwd_f32(x, params, nh, save_hidden=False)
+        assert none16 is None
+        np.testing.assert_array_equal(N(out32b), N(out32))
+        # backward over the same tiles (double-buffered operand prefetch, in-place activation gradients,
+        # weight gradients resident in TMEM across the CTA's tiles) against the CUDA-core twin
+        dout = T((rng.standard_normal((n, 16)) * 0.1).astype(np.float16))
+        din, dp = ops.mlp_bwd(dout, x, hid0, params, nh, need_din=True, impl="tc")
+        din0, dp0 = ops.mlp_bwd(dout, x, hid0, params, nh, need_din=True, impl="v0")
+        assert_close(N(din).astype(np.float32), N(din0).astype(np.float32), rtol=4e-3, atol_frac=2e-3, name=f"din n={n}")
+        assert_close(N(dp), N(dp0), rtol=3e-3, atol_frac=2e-3, name=f"dparams n={n}")
+
+
 def test_fused_field_matches_unfused(scene, oracle, hash_params):
     """f2b_field_fwd (encode fused into the tcgen05 MLP) == f2b_hash_fwd -> f2b_mlp_fwd_tc, bit for bit."""
     from f2nerf_b200 import ops
