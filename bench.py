@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
                                   nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
-                time.sleep(0.1)
+                time.sleep(0.2)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)[:120]
 
@@ -174,21 +174,36 @@ def run_ours(args):
         train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
     barrier()
     clocks.rows.clear()                          # keep only samples taken under the timed regions
-    launches0 = _lib.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n_samples = n_kept = 0
-    walls = []
-    for _ in range(args.steps):
-        w0 = time.perf_counter()
-        loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
-        n_samples += prob["renderer"].sample_result_.pts.shape[0]
-        n_kept += res.weights.shape[0]
-        walls.append(round((time.perf_counter() - w0) * 1e3, 2))
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.LAUNCHES - launches0
+    def timed_loop():
+        barrier()
+        l0 = _lib.LAUNCHES
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        ns = nk = 0
+        w = []
+        for _ in range(args.steps):
+            w0 = time.perf_counter()
+            loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
+            ns += prob["renderer"].sample_result_.pts.shape[0]
+            nk += res.weights.shape[0]
+            w.append(round((time.perf_counter() - w0) * 1e3, 2))
+        eb.record()
+        barrier()
+        return ea.elapsed_time(eb), w, ns, nk, _lib.LAUNCHES - l0
+
+    # A step whose host wall time is far off the median (seen on fresh boxes: one NVML poll of the clock sampler
+    # holding the driver lock for ~40 ms while the main thread launches) makes the whole K-step number a
+    # measurement of that stall: such a run is rejected and the K steps are timed ONCE more; both are reported.
+    attempts = []
+    for _ in range(2):
+        ms, walls, n_samples, n_kept, launches = timed_loop()
+        med = sorted(walls)[len(walls) // 2]
+        outlier = max(walls) > 2.5 * med and max(walls) - med > 5.0
+        attempts.append({"ms_per_step": ms / args.steps, "host_wall_ms_per_step": walls, "rejected": bool(outlier)})
+        if not outlier:
+            break
+        if world > 1:
+            break                                 # ranks must take the same branch: no re-measure under torchrun
     # ---- per-kernel CUDA-event trace over the same steps (separate loop: event pairs around every C-ABI call) --
     _lib.TRACE = []
     for _ in range(args.steps):
@@ -253,7 +268,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in (h_o, h_d, h_cam, h_gt))) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "host_wall_ms_per_step": walls,
+        "host_wall_ms_per_step": walls, "timing_attempts": attempts,
         "clocks": clocks.summary(),
         "roofline": roof,
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in

@@ -15,12 +15,14 @@
 #include "common.cuh"
 #include "hash.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace f2b {
 using namespace tc;
 
 constexpr int kFT = 128;
 constexpr int kFieldTmemCols = 64;
+constexpr int kFieldDefaultMinB = 4;   // see DESIGN.md: 4 = max loads in flight per thread, 6 = max resident warps
 
 struct FieldSmem {
   static constexpr int A0 = 0;          // [128 x 32] f16 SW64   8 KB
@@ -31,8 +33,8 @@ struct FieldSmem {
   static constexpr int BYTES = 30720 + 128 + 1024;
 };
 
-template <bool LOGIT_ONLY>
-__global__ void __launch_bounds__(kFT)
+template <bool LOGIT_ONLY, int MINB>
+__global__ void __launch_bounds__(kFT, MINB)
 field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_pool,
                  const float* __restrict__ bias_pool, int n_volumes, int local_size,
                  const __half* __restrict__ params, const float* __restrict__ pts, const int* __restrict__ vol,
@@ -81,11 +83,8 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
       for (int l = 0; l < 16; l++) enc[l] = 0u;
     }
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const uint4 v = make_uint4(enc[4 * c], enc[4 * c + 1], enc[4 * c + 2], enc[4 * c + 3]);
-      *reinterpret_cast<uint4*>(sm + FieldSmem::A0 + sw64_off(tid, c)) = v;
-      if (feat_save && valid) reinterpret_cast<uint4*>(feat_save + size_t(p) * 32)[c] = v;
-    }
+    for (int c = 0; c < 4; c++)
+      *reinterpret_cast<uint4*>(sm + FieldSmem::A0 + sw64_off(tid, c)) = make_uint4(enc[4 * c], enc[4 * c + 1], enc[4 * c + 2], enc[4 * c + 3]);
     fence_async_smem();
     __syncthreads();
     // ---- layer 0 on the tensor pipe -------------------------------------------------------------------
@@ -94,6 +93,15 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
 #pragma unroll
       for (int k = 0; k < 2; k++) mma_f16(tmem, kmajor_desc(a0 + 32 * k, 64), kmajor_desc(w0 + 32 * k, 64), idesc64, k);
       mma_commit(mbar);
+    }
+    if (feat_save) {                                              // whole-line copy-out of the tile while the MMA reads it
+      const int rows = min(kFT, n_pts - tile * kFT);
+      uint4* dst = reinterpret_cast<uint4*>(feat_save + size_t(tile) * kFT * 32);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = tid + kFT * j, r = c >> 2;
+        if (r < rows) dst[c] = *reinterpret_cast<const uint4*>(sm + FieldSmem::A0 + sw64_off(r, c & 3));
+      }
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
@@ -111,10 +119,6 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
       }
       *reinterpret_cast<uint4*>(sm + FieldSmem::A1 + sw128_off(tid, 2 * q)) = v[0];
       *reinterpret_cast<uint4*>(sm + FieldSmem::A1 + sw128_off(tid, 2 * q + 1)) = v[1];
-      if (!LOGIT_ONLY && hidden_save && valid) {
-        uint4* dst = reinterpret_cast<uint4*>(hidden_save + size_t(p) * 64) + 2 * q;
-        dst[0] = v[0]; dst[1] = v[1];
-      }
     }
     fence_before_sync();
     fence_async_smem();
@@ -125,6 +129,15 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
 #pragma unroll
       for (int k = 0; k < 4; k++) mma_f16(tmem, kmajor_desc(a1 + 32 * k, 128), kmajor_desc(wo + 32 * k, 128), idesc16, k);
       mma_commit(mbar);
+    }
+    if (!LOGIT_ONLY && hidden_save) {
+      const int rows = min(kFT, n_pts - tile * kFT);
+      uint4* dst = reinterpret_cast<uint4*>(hidden_save + size_t(tile) * kFT * 64);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int c = tid + kFT * j, r = c >> 3;
+        if (r < rows) dst[c] = *reinterpret_cast<const uint4*>(sm + FieldSmem::A1 + sw128_off(r, c & 7));
+      }
     }
     mbar_wait(mbar, phase); phase ^= 1;
     fence_after_sync();
@@ -164,17 +177,21 @@ extern "C" int f2b_field_fwd(const void* table_f16, const int* prim_pool, const 
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   const int n_tiles = div_up(n_pts, kFT);
-  const int grid = n_tiles < sms * 6 ? n_tiles : sms * 6;
-  if (logit_only) {
-    cudaFuncSetAttribute(field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);
-    field_fwd_kernel<true><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(
-        (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, (const __half*)mlp_params_f16, pts, vol,
-        vol_stride, n_pts, out_f32, (__half*)feat_save_f16, nullptr);
-  } else {
-    cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);
-    field_fwd_kernel<false><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(
-        (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, (const __half*)mlp_params_f16, pts, vol,
-        vol_stride, n_pts, out_f32, (__half*)feat_save_f16, (__half*)hidden_save_f16);
+  static int minb = -1;                                           // resident CTAs per SM the kernel is compiled for
+  if (minb < 0) { const char* e = getenv("F2B_FIELD_MINB"); minb = e ? atoi(e) : kFieldDefaultMinB; }
+#define F2B_FIELD_LAUNCH(LO, MB)                                                                                      \
+  {                                                                                                                   \
+    const int grid = n_tiles < sms * MB ? n_tiles : sms * MB;                                                         \
+    cudaFuncSetAttribute(field_fwd_kernel<LO, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);    \
+    field_fwd_kernel<LO, MB><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(                                     \
+        (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, (const __half*)mlp_params_f16, pts, vol, \
+        vol_stride, n_pts, out_f32, (__half*)feat_save_f16, LO ? nullptr : (__half*)hidden_save_f16);                 \
   }
+  if (logit_only) {
+    if (minb >= 6) F2B_FIELD_LAUNCH(true, 6) else if (minb == 5) F2B_FIELD_LAUNCH(true, 5) else F2B_FIELD_LAUNCH(true, 4)
+  } else {
+    if (minb >= 6) F2B_FIELD_LAUNCH(false, 6) else if (minb == 5) F2B_FIELD_LAUNCH(false, 5) else F2B_FIELD_LAUNCH(false, 4)
+  }
+#undef F2B_FIELD_LAUNCH
   return check_launch("f2b_field_fwd");
 }

@@ -44,6 +44,8 @@ hash_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_p
 // reductions red.global.add.v2.f32 — up to 32x fewer L2 atomics at the coarse levels; fine levels (every
 // lane its own run) take the direct path.  fp32 accumulation (the reference accumulates fp16 atomics of
 // grad*128, Hash3DAnchored.cu:145-151, and casts/divides afterwards); zero-gradient rows are skipped (:149).
+constexpr int kDirectHeads = 24;
+
 template <bool GRAD_F16>
 __global__ void __launch_bounds__(256)
 hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bias_pool, int n_volumes,
@@ -88,7 +90,7 @@ hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bia
   const bool head = (lane == 0) || !live || c.cell[0] != pcx || c.cell[1] != pcy || c.cell[2] != pcz || v != prev_v;
   const unsigned heads = __ballot_sync(0xffffffffu, head);
   float* base = grad_table + size_t(l) * local_size;
-  if (__popc(heads) > 20) {                                   // mostly singleton runs: direct reductions
+  if (__popc(heads) > kDirectHeads) {                         // mostly singleton runs: direct reductions
     if (live) {
 #pragma unroll
       for (int k = 0; k < 8; k++)
@@ -102,8 +104,11 @@ hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bia
   float s[16];
 #pragma unroll
   for (int k = 0; k < 8; k++) { s[2 * k] = c.w[k] * g0; s[2 * k + 1] = c.w[k] * g1; }
+  // only ceil(log2(longest run)) stages move data; the rest would be no-ops (warp-uniform early exit)
+  const int max_run = __reduce_max_sync(0xffffffffu, lane - run_start + 1);
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
+    if (o >= max_run) break;
     const bool take = (lane - o) >= run_start;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
