@@ -85,8 +85,14 @@ class Renderer:
                                                    logit_only=True, save_feat=True)
             weights0, alphas0, keep, new_bounds, total = ops.early_stop(logit_all, 1, sr.dt, sr.pts_idx_bounds)
             n_kept = int(total.item())                                               # sync 2
+            side = None
             if train:
-                sampler.UpdateOctNodes(sr, weights0, alphas0)
+                # octree occupancy votes only feed the NEXT iteration's march: run them beside the gradient pass
+                main = torch.cuda.current_stream(dev)
+                side = self._side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sampler.UpdateOctNodes(sr, weights0, alphas0)
                 gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
             n_edge = 2 * N_EDGE_PTS if train else 0
             feat_q = torch.empty((n_kept + n_edge, 32), dtype=torch.float16, device=dev)
@@ -116,7 +122,15 @@ class Renderer:
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, *args)
         if not train:
             edge_feats = None
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)      # joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, es.first_oct_dis, disparity, edge_feats, depth, weights, new_bounds)
+
+    def _side_stream(self, dev):
+        st = getattr(self, "_side_", None)
+        if st is None or st.device != torch.device(dev):
+            st = self._side_ = torch.cuda.Stream(device=dev)
+        return st
 
     # ------------------------------------------------------------------------------------------
     def States(self):
@@ -168,6 +182,9 @@ class _RenderFunction(torch.autograd.Function):
     def backward(ctx, d_colors, d_disp, d_depth, d_weights, d_edge):
         renderer, es, n_kept = ctx.renderer, ctx.es, ctx.n_kept
         field, shader, gdp = renderer.scene_field_, renderer.shader_, renderer.global_data_pool_
+        if ctx.pack is None:
+            raise RuntimeError("Renderer.Render backward: the saved activations were released by a previous backward "
+                               "(like tiny-cuda-nn's context, TCNNWP.cpp:207, the graph can be traversed once)")
         (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
          rgb) = ctx.pack
         if f_hidden is None:
@@ -206,6 +223,7 @@ class _RenderFunction(torch.autograd.Function):
         # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
         bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
         renderer.nonfinite_flag_ = bad
+        ctx.pack = None                               # saved activations (~1 GB at 4 M samples) die with the backward, not with `res`
         return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None, None
 
 
