@@ -184,7 +184,7 @@ def run_ours(args):
         for _ in range(args.steps):
             w0 = time.perf_counter()
             loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
-            ns += prob["renderer"].sample_result_.pts.shape[0]
+            ns += prob["renderer"].n_sampled_pts_
             nk += res.weights.shape[0]
             w.append(round((time.perf_counter() - w0) * 1e3, 2))
         eb.record()

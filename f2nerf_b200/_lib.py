@@ -56,6 +56,7 @@ SIGNATURES = {
     "f2b_mlp_fwd_tc": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_bwd_tc": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_field_fwd": [_P, _P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P],
+    "f2b_field_fwd_slots": [_P, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P],
     "f2b_set_mlp_impl": [c_int],
     "f2b_get_mlp_impl": [],
     "f2b_cast_f32_to_f16": [_P, _P, c_i64, c_float, _P],
@@ -68,6 +69,10 @@ SIGNATURES = {
     "f2b_shader_prep_bwd": [_P, _P, _P, c_int, c_float, _P, _P, _P],
     "f2b_shader_prep_bwd_f16": [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P],
     "f2b_early_stop": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_early_stop_rays": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "f2b_count_scan": [_P, c_int, _P, _P, _P],
+    "f2b_slot_bounds": [_P, c_int, c_int, c_int, _P, _P],
+    "f2b_compact_slots": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_compact_samples": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_composite_fwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "f2b_composite_bwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, _P],

@@ -112,6 +112,51 @@ compact_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ old_bou
   }
 }
 
+// Same compaction straight out of the one-pass march's scratch slots (ray r owns slots
+// [r*slot, r*slot + count[r]); 28 B/sample there): directions are the ray's, anchors[:,2] is 0 — the
+// all-sample SampleResultFlex the reference materialises between march and early stop is never built.
+__global__ void __launch_bounds__(256)
+compact_slots_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ slot_bounds,
+                     const int* __restrict__ new_bounds, int n_rays, const float* __restrict__ rays_d,
+                     const float* __restrict__ s_pts, const float* __restrict__ s_dt, const float* __restrict__ s_t,
+                     const int* __restrict__ s_anchors, const uint4* __restrict__ feat, float* __restrict__ pts_o,
+                     float* __restrict__ dirs_o, float* __restrict__ dt_o, float* __restrict__ t_o,
+                     int* __restrict__ anchors_o, uint4* __restrict__ feat_o) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= n_rays) return;
+  const int beg = slot_bounds[2 * ray], end = slot_bounds[2 * ray + 1];
+  const float d0 = __ldg(rays_d + ray * 3), d1 = __ldg(rays_d + ray * 3 + 1), d2 = __ldg(rays_d + ray * 3 + 2);
+  int out = new_bounds[2 * ray];
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    const bool k = (i < end) && keep[i];
+    const unsigned m = __ballot_sync(kFull, k);
+    if (k) {
+      const size_t o = size_t(out) + __popc(m & ((1u << lane) - 1u));
+      const size_t s = size_t(i);
+      pts_o[o * 3] = s_pts[s * 3]; pts_o[o * 3 + 1] = s_pts[s * 3 + 1]; pts_o[o * 3 + 2] = s_pts[s * 3 + 2];
+      dirs_o[o * 3] = d0; dirs_o[o * 3 + 1] = d1; dirs_o[o * 3 + 2] = d2;
+      anchors_o[o * 3] = s_anchors[s * 2]; anchors_o[o * 3 + 1] = s_anchors[s * 2 + 1]; anchors_o[o * 3 + 2] = 0;
+      dt_o[o] = s_dt[s];
+      t_o[o] = s_t[s];
+      if (feat) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) feat_o[o * 4 + c] = feat[s * 4 + c];
+      }
+    }
+    out += __popc(m);
+  }
+}
+
+__global__ void slot_bounds_kernel(const int* __restrict__ counts, int n_rays, int slot, int first_ray, int* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const int b = (first_ray + r) * slot;
+  out[2 * r] = b;
+  out[2 * r + 1] = b + counts[r];
+}
+
 // ---- forward composite ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ logit, int logit_stride, const float* __restrict__ rgb,
@@ -341,6 +386,42 @@ extern "C" int f2b_early_stop(const float* logit, int logit_stride, const float*
                                                       alphas, keep, ray_counts);
   scan_counts_kernel<<<1, 1024, 0, st>>>(ray_counts, n_rays, new_bounds, total_kept);
   return check_launch("f2b_early_stop");
+}
+
+extern "C" int f2b_early_stop_rays(const float* logit, int logit_stride, const float* dt, const int* pts_idx_bounds,
+                                   int n_rays, float* weights, float* alphas, uint8_t* keep, int* ray_counts, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(logit && dt && pts_idx_bounds && weights && alphas && keep && ray_counts, "f2b_early_stop_rays: null pointer");
+  early_stop_kernel<<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(logit, logit_stride, dt, pts_idx_bounds, n_rays,
+                                                                     weights, alphas, keep, ray_counts);
+  return check_launch("f2b_early_stop_rays");
+}
+
+extern "C" int f2b_count_scan(const int* counts, int n, int* bounds, int* total, void* stream) {
+  F2B_REQUIRE(bounds && total && (counts || n <= 0), "f2b_count_scan: null pointer");
+  scan_counts_kernel<<<1, 1024, 0, as_stream(stream)>>>(counts, n > 0 ? n : 0, bounds, total);
+  return check_launch("f2b_count_scan");
+}
+
+extern "C" int f2b_slot_bounds(const int* ray_counts, int n_rays, int slot_size, int first_ray, int* slot_bounds, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(ray_counts && slot_bounds && slot_size > 0, "f2b_slot_bounds: bad argument");
+  slot_bounds_kernel<<<div_up(n_rays, 256), 256, 0, as_stream(stream)>>>(ray_counts, n_rays, slot_size, first_ray, slot_bounds);
+  return check_launch("f2b_slot_bounds");
+}
+
+extern "C" int f2b_compact_slots(const uint8_t* keep, const int* slot_bounds, const int* new_bounds, int n_rays,
+                                 const float* rays_d, const float* s_pts, const float* s_dt, const float* s_t,
+                                 const int* s_anchors, const void* feat_slots_f16, float* pts_o, float* dirs_o,
+                                 float* dt_o, float* t_o, int* anchors_o, void* feat_o_f16, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(keep && slot_bounds && new_bounds && rays_d && s_pts && s_dt && s_t && s_anchors && pts_o && dirs_o && dt_o &&
+                  t_o && anchors_o, "f2b_compact_slots: null pointer");
+  F2B_REQUIRE(!feat_slots_f16 || feat_o_f16, "f2b_compact_slots: feat_slots_f16 without feat_o_f16");
+  compact_slots_kernel<<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(
+      keep, slot_bounds, new_bounds, n_rays, rays_d, s_pts, s_dt, s_t, s_anchors, (const uint4*)feat_slots_f16, pts_o, dirs_o,
+      dt_o, t_o, anchors_o, (uint4*)feat_o_f16);
+  return check_launch("f2b_compact_slots");
 }
 
 extern "C" int f2b_compact_samples(const uint8_t* keep, const int* old_bounds, const int* new_bounds, int n_rays,

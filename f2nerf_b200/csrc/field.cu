@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(kFT, MINB)
 field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_pool,
                  const float* __restrict__ bias_pool, int n_volumes, int local_size,
                  const __half* __restrict__ params, const float* __restrict__ pts, const int* __restrict__ vol,
-                 int vol_stride, int n_pts, float* __restrict__ out, __half* __restrict__ feat_save,
-                 __half* __restrict__ hidden_save) {
+                 int vol_stride, int n_pts, const int* __restrict__ slot_counts, int slot_size,
+                 float* __restrict__ out, __half* __restrict__ feat_save, __half* __restrict__ hidden_save) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + FieldSmem::BAR);
@@ -72,7 +72,14 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
   const int n_tiles = (n_pts + kFT - 1) / kFT;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kFT + tid;
-    const bool valid = p < n_pts;
+    bool valid = p < n_pts;
+    if (slot_counts) {
+      // slot layout (the one-pass march's scratch): ray r owns slots [r*slot_size, r*slot_size + count[r]).
+      // slot_size is a multiple of the tile, so a tile lies inside one ray: skip it whole when it is past the count.
+      const int t0 = tile * kFT, ray = t0 / slot_size, cnt = __ldg(slot_counts + ray);
+      if (t0 - ray * slot_size >= cnt) continue;                    // CTA-uniform
+      valid = valid && (p - ray * slot_size) < cnt;
+    }
     // ---- encode my sample: 16 levels x 8 corner gathers -> 32 halfs in registers ------------------
     uint32_t enc[16];
     if (valid) {
@@ -167,10 +174,35 @@ field_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_
 
 using namespace f2b;
 
+static int field_fwd_launch(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
+                            int local_size, const void* mlp_params_f16, const float* pts, const int* vol,
+                            int vol_stride, int n_pts, const int* slot_counts, int slot_size, int logit_only,
+                            float* out_f32, void* feat_save_f16, void* hidden_save_f16, void* stream);
+
 extern "C" int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
                              int local_size, const void* mlp_params_f16, const float* pts, const int* vol,
                              int vol_stride, int n_pts, int logit_only, float* out_f32, void* feat_save_f16,
                              void* hidden_save_f16, void* stream) {
+  return field_fwd_launch(table_f16, prim_pool, bias_pool, n_volumes, local_size, mlp_params_f16, pts, vol, vol_stride,
+                          n_pts, nullptr, 0, logit_only, out_f32, feat_save_f16, hidden_save_f16, stream);
+}
+
+extern "C" int f2b_field_fwd_slots(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
+                                   int local_size, const void* mlp_params_f16, const float* slot_pts, const int* slot_vol,
+                                   int vol_stride, const int* ray_counts, int n_rays, int slot_size, int logit_only,
+                                   float* out_f32, void* feat_save_f16, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(ray_counts && slot_size > 0 && (slot_size % kFT) == 0, "f2b_field_fwd_slots: slot_size must be a positive multiple of 128");
+  F2B_REQUIRE(int64_t(n_rays) * slot_size < (int64_t(1) << 31), "f2b_field_fwd_slots: n_rays * slot_size overflows int32");
+  return field_fwd_launch(table_f16, prim_pool, bias_pool, n_volumes, local_size, mlp_params_f16, slot_pts, slot_vol,
+                          vol_stride, n_rays * slot_size, ray_counts, slot_size, logit_only, out_f32, feat_save_f16, nullptr,
+                          stream);
+}
+
+static int field_fwd_launch(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
+                            int local_size, const void* mlp_params_f16, const float* pts, const int* vol,
+                            int vol_stride, int n_pts, const int* slot_counts, int slot_size, int logit_only,
+                            float* out_f32, void* feat_save_f16, void* hidden_save_f16, void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(table_f16 && prim_pool && bias_pool && mlp_params_f16 && pts && vol && out_f32, "f2b_field_fwd: null pointer");
   F2B_REQUIRE(n_volumes > 0 && local_size > 0 && (local_size % 2) == 0, "f2b_field_fwd: bad n_volumes/local_size");
@@ -185,7 +217,8 @@ extern "C" int f2b_field_fwd(const void* table_f16, const int* prim_pool, const 
     cudaFuncSetAttribute(field_fwd_kernel<LO, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::BYTES);    \
     field_fwd_kernel<LO, MB><<<grid, kFT, FieldSmem::BYTES, as_stream(stream)>>>(                                     \
         (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, (const __half*)mlp_params_f16, pts, vol, \
-        vol_stride, n_pts, out_f32, (__half*)feat_save_f16, LO ? nullptr : (__half*)hidden_save_f16);                 \
+        vol_stride, n_pts, slot_counts, slot_size, out_f32, (__half*)feat_save_f16,                                  \
+        LO ? nullptr : (__half*)hidden_save_f16);                                                                     \
   }
   if (logit_only) {
     if (minb >= 6) F2B_FIELD_LAUNCH(true, 6) else if (minb == 5) F2B_FIELD_LAUNCH(true, 5) else F2B_FIELD_LAUNCH(true, 4)

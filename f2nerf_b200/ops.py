@@ -229,6 +229,30 @@ def early_stop(logit, logit_stride, dt, bounds):
     return weights, alphas, keep, new_bounds, total
 
 
+def field_fwd_slots(table_f16, prim_pool, bias_pool, n_volumes, local_size, params_f16, slot_pts, slot_anchors, counts, n_rays,
+                    slot, out_logit, feat_slots):
+    """Early-stop field pass over the march's slot layout (logit only); all tensor arguments may be ray-chunk views."""
+    call("f2b_field_fwd_slots", table_f16, prim_pool, bias_pool, int(n_volumes), int(local_size), params_f16, slot_pts,
+         slot_anchors, int(slot_anchors.shape[1]), counts, int(n_rays), int(slot), 1, out_logit, feat_slots, stream())
+
+
+def early_stop_rays(logit, logit_stride, dt, bounds, weights, alphas, keep, counts):
+    call("f2b_early_stop_rays", logit, int(logit_stride), dt, bounds, bounds.shape[0], weights, alphas, keep, counts, stream())
+
+
+def count_scan(counts, n):
+    bounds = dev_empty((n, 2), I32, counts)
+    total = torch.zeros((1,), dtype=I32, device=counts.device)
+    call("f2b_count_scan", counts, int(n), bounds, total, stream())
+    return bounds, total
+
+
+def compact_slots(keep, slot_bounds, new_bounds, rays_d, s_pts, s_dt, s_t, s_anchors, feat_slots, outs, feat_out):
+    """outs = (pts, dirs, dt, t, anchors) destination arrays indexed by ``new_bounds``; bounds / rays_d may be chunk views."""
+    call("f2b_compact_slots", keep, slot_bounds, new_bounds, slot_bounds.shape[0], rays_d, s_pts, s_dt, s_t, s_anchors,
+         feat_slots, *outs, feat_out, stream())
+
+
 def compact_samples(keep, old_bounds, new_bounds, n_kept, pts, dirs, dt, t, anchors, feat=None, feat_out=None):
     outs = (dev_empty((n_kept, 3), F32, pts), dev_empty((n_kept, 3), F32, pts), dev_empty((n_kept,), F32, pts),
             dev_empty((n_kept,), F32, pts), dev_empty((n_kept, 3), I32, pts))

@@ -7,6 +7,7 @@ ONE autograd node to the four leaves the trainer optimises (``feat_pool_``, the 
 (composite bwd -> shader MLP bwd -> field MLP bwd -> hash scatter) instead of ~60 autograd nodes.
 Host syncs per call: 2 (sample total, survivor total) against the reference's >= 11 ``.item()`` calls.
 """
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -15,7 +16,7 @@ import torch
 from . import ops
 from .field import field_backward, field_forward, field_forward_from_features
 from .rng import burn_mlp_output, burn_rand
-from .sampler import TRAIN, VALIDATE, SampleResultFlex
+from .sampler import TRAIN, VALIDATE, LazySampleResult, SampleResultFlex
 
 N_EDGE_PTS = 8192
 
@@ -61,45 +62,73 @@ class Renderer:
         field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
         n_rays, dev = rays_o.shape[0], rays_o.device
         train = gdp.mode_ == TRAIN
-        sr = sampler.GetSamples(rays_o, rays_d, bounds)
-        self.sample_result_ = sr
-        n_all = sr.pts.shape[0]
-        if train and n_rays > 0:
-            gdp.sampled_pts_per_ray_ = gdp.sampled_pts_per_ray_ * .9 + (n_all / n_rays) * .1
+        # ---- phase 1: march -> early-stop field pass -> survivors, in the march's slot layout (no host sync) ----
+        slots = sampler.begin_march(rays_o, rays_d)                  # draws the ray noise (RNG order: noise, bg, ...)
+        self.sample_result_ = LazySampleResult(slots)                # the reference-layout view, built only on access
         bg = self._bg(n_rays, dev)
-        if n_all <= 0:
-            if train:
-                gdp.meaningful_sampled_pts_per_ray_ *= .9
+        if n_rays <= 0:
             z = torch.zeros
-            return RenderResult(bg, z((n_rays, 1), device=dev), z((n_rays,), device=dev), None,
-                                torch.full((n_rays,), 512., device=dev), None, None)
-
-        # ---- early stop: inference only (Renderer.cpp:107-150) --------------------------------
+            return RenderResult(bg, z((0, 1), device=dev), z((0,), device=dev), None, z((0,), device=dev), None, None)
+        S = slots.slot
         with torch.no_grad():
             table16 = field.table_f16()
             fparams16 = field.mlp_.params_f16()
             # the encoded features of ALL samples are kept: survivors re-use them in the gradient pass instead of
             # gathering the table a second time (identical values: same points, same table)
+            logit_s = self._buf("logit", (n_rays * S,), torch.float32, dev)
+            feat_s = self._buf("feat", (n_rays * S, 32), torch.float16, dev)
+            weights0 = self._buf("w0", (n_rays * S,), torch.float32, dev)
+            alphas0 = self._buf("a0", (n_rays * S,), torch.float32, dev)
+            keep = self._buf("keep", (n_rays * S,), torch.uint8, dev)
+            kept_counts = self._buf("kept", (n_rays,), torch.int32, dev)
+            main = torch.cuda.current_stream(dev)
+            chunks = self._ray_chunks(n_rays)
+            lanes = [main] + [self._side_stream(dev, i) for i in range(1, len(chunks))]
+            ready = torch.cuda.Event()
+            ready.record(main)                                       # inputs / table / noise are ready here
+            for (r0, r1), st in zip(chunks, lanes):                  # ray chunks on their own streams: chunk k's field
+                if st is not main:                                   # pass (memory latency) overlaps chunk k+1's march (issue)
+                    st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    sampler.march_rays(slots, r0, r1)
+                    ops.field_fwd_slots(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_,
+                                        fparams16, slots.s_pts[r0 * S:r1 * S], slots.s_anchors[r0 * S:r1 * S],
+                                        slots.counts[r0:r1], r1 - r0, S, logit_s[r0 * S:r1 * S], feat_s[r0 * S:r1 * S])
+                    ops.early_stop_rays(logit_s, 1, slots.s_dt, slots.slot_bounds[r0:r1], weights0, alphas0, keep,
+                                        kept_counts[r0:r1])
+            for st in lanes[1:]:
+                main.wait_stream(st)
+            new_bounds, total = ops.count_scan(kept_counts, n_rays)
+            vals = torch.cat([total] + [t.reshape(-1) for t in slots.totals]).tolist()   # THE host sync of the step
+            n_kept, n_all, n_all_oct = int(vals[0]), int(sum(vals[1::2])), int(sum(vals[2::2]))
+            sampler.note_totals(n_rays, n_all_oct)
+            slots.noted = True
+            self.n_sampled_pts_, self.n_kept_pts_ = n_all, n_kept     # host-side counts of this call (no extra sync)
+            if train:
+                gdp.sampled_pts_per_ray_ = gdp.sampled_pts_per_ray_ * .9 + (n_all / n_rays) * .1
+            if n_all <= 0:
+                if train:
+                    gdp.meaningful_sampled_pts_per_ray_ *= .9
+                z = torch.zeros
+                return RenderResult(bg, z((n_rays, 1), device=dev), z((n_rays,), device=dev), None,
+                                    torch.full((n_rays,), 512., device=dev), None, None)
             burn_mlp_output(n_all, dev)                   # RNG parity: the reference's MLP output is a torch::rand (rng.py)
-            logit_all, feat_all, _ = field_forward(field, table16, fparams16, sr.pts, sr.anchors, 3, save=False,
-                                                   logit_only=True, save_feat=True)
-            weights0, alphas0, keep, new_bounds, total = ops.early_stop(logit_all, 1, sr.dt, sr.pts_idx_bounds)
-            n_kept = int(total.item())                                               # sync 2
             side = None
             if train:
                 # octree occupancy votes only feed the NEXT iteration's march: run them beside the gradient pass
-                main = torch.cuda.current_stream(dev)
-                side = self._side_stream(dev)
+                side = self._side_stream(dev, 1)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    sampler.UpdateOctNodes(sr, weights0, alphas0)
+                    sampler.update_oct_nodes_raw(slots.slot_bounds, slots.s_anchors, weights0, alphas0)
                 gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
             n_edge = 2 * N_EDGE_PTS if train else 0
             feat_q = torch.empty((n_kept + n_edge, 32), dtype=torch.float16, device=dev)
-            pts, dirs, dt, t, anchors = ops.compact_samples(keep, sr.pts_idx_bounds, new_bounds, n_kept, sr.pts,
-                                                            sr.dirs, sr.dt, sr.t, sr.anchors, feat_all, feat_q)
-            del feat_all
-            es = SampleResultFlex(pts, dirs, dt, t, anchors, new_bounds, sr.first_oct_dis.clone())
+            f32 = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+            pts, dirs, dt, t = f32(n_kept, 3), f32(n_kept, 3), f32(n_kept), f32(n_kept)
+            anchors = torch.empty((n_kept, 3), dtype=torch.int32, device=dev)
+            ops.compact_slots(keep, slots.slot_bounds, new_bounds, slots.rays_d, slots.s_pts, slots.s_dt, slots.s_t,
+                              slots.s_anchors, feat_s, (pts, dirs, dt, t, anchors), feat_q)
+            es = SampleResultFlex(pts, dirs, dt, t, anchors, new_bounds, slots.first_oct_dis.clone())
             if train:                                                                 # TV-loss edge points
                 edge_pts, edge_anchors = sampler.GetEdgeSamples(N_EDGE_PTS)
                 e_pts, e_anc = edge_pts.reshape(N_EDGE_PTS * 2, 3), edge_anchors.reshape(N_EDGE_PTS * 2)
@@ -126,11 +155,31 @@ class Renderer:
             torch.cuda.current_stream(dev).wait_stream(side)      # joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, es.first_oct_dis, disparity, edge_feats, depth, weights, new_bounds)
 
-    def _side_stream(self, dev):
-        st = getattr(self, "_side_", None)
-        if st is None or st.device != torch.device(dev):
-            st = self._side_ = torch.cuda.Stream(device=dev)
-        return st
+    def _side_stream(self, dev, i=1):
+        pool = self.__dict__.setdefault("_streams_", {})
+        key = (torch.device(dev).index, i)
+        if key not in pool:
+            pool[key] = torch.cuda.Stream(device=dev)
+        return pool[key]
+
+    def _buf(self, name, shape, dtype, dev):
+        """Persistent slot-layout work buffers (grown on demand; no allocator traffic in steady state)."""
+        pool = self.__dict__.setdefault("_bufs_", {})
+        n = 1
+        for d in shape:
+            n *= d
+        t = pool.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype or t.device != torch.device(dev):
+            t = pool[name] = torch.empty((max(n, 1),), dtype=dtype, device=dev)
+        return t[:n].view(*shape)
+
+    def _ray_chunks(self, n_rays):
+        """Ray ranges marched on separate streams (F2B_RAY_CHUNKS / ``ray_chunks_``; 1 = single stream)."""
+        if not hasattr(self, "ray_chunks_"):
+            self.ray_chunks_ = int(os.environ.get("F2B_RAY_CHUNKS", "1"))
+        k = max(1, min(int(self.ray_chunks_), 4, (n_rays + 255) // 256))
+        step = -(-n_rays // k)
+        return [(r0, min(r0 + step, n_rays)) for r0 in range(0, n_rays, step)]
 
     # ------------------------------------------------------------------------------------------
     def States(self):

@@ -32,6 +32,45 @@ class SampleResultFlex:
     first_oct_dis: torch.Tensor    # [n_rays, 1]
 
 
+class SlotSamples:
+    """Result of the one-pass march in its native layout: ray ``r`` owns slots ``[r*1024, r*1024 + counts[r])`` of
+    the sampler's persistent scratch (pts, dt, t, anchors[0:2]; 28 B/sample).  The renderer runs the early-stop pass
+    on this layout directly, so the cumsum / host sync / gather of ``PersSampler::GetSamples`` (PersSampler.cu:395-434)
+    only happens when somebody asks for the reference's ``SampleResultFlex`` (:meth:`PersSampler.materialize`).
+    Valid until the sampler's next march."""
+    slot = MAX_SAMPLE_PER_RAY
+
+    def __init__(self, sampler, rays_o, rays_d, noise, bufs, generation):
+        self.sampler, self.rays_o, self.rays_d, self.noise, self.generation = sampler, rays_o, rays_d, noise, generation
+        self.n_rays = rays_o.shape[0]
+        n = self.n_rays * self.slot
+        self.s_pts, self.s_dt, self.s_t, self.s_anchors = bufs[0][:n], bufs[1][:n], bufs[2][:n], bufs[3][:n]
+        dev = rays_o.device
+        R = max(self.n_rays, 1)
+        self.counts = torch.empty((R,), dtype=torch.int32, device=dev)
+        self.chunk_bounds = torch.empty((R, 2), dtype=torch.int32, device=dev)      # chunk-local cumsum (unused by the renderer)
+        self.slot_bounds = torch.empty((self.n_rays, 2), dtype=torch.int32, device=dev)
+        self.first_oct_dis = torch.empty((self.n_rays, 1), dtype=torch.float32, device=dev)
+        self.totals = []                                                            # one device [2] tensor per marched chunk
+
+
+class LazySampleResult:
+    """``Renderer::sample_result_`` on demand: attribute access materialises the reference-layout SampleResultFlex
+    (one scan + host sync + gather) from the slot layout; the training path never touches it."""
+
+    def __init__(self, slots):
+        object.__setattr__(self, "_slots", slots)
+        object.__setattr__(self, "_flex", None)
+
+    def _get(self):
+        if self._flex is None:
+            object.__setattr__(self, "_flex", self._slots.sampler.materialize(self._slots))
+        return self._flex
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+
 class GlobalDataPool:
     """The cross-module scalars of ``GlobalDataPool`` (src/Utils/GlobalDataPool.h:10-32) the path reads/writes."""
 
@@ -90,21 +129,58 @@ class PersSampler:
     def GetSamples(self, rays_o_raw, rays_d_raw, bounds_raw=None, rays_noise=None):
         """PersSampler::GetSamples (PersSampler.cu:317-434).  ``bounds_raw`` is ignored like in the
         reference (it marches [global_near_, 1e8]).  One host sync (sample total) instead of two."""
+        slots = self.begin_march(rays_o_raw, rays_d_raw, rays_noise)
+        self.march_rays(slots, 0, slots.n_rays)
+        return self.materialize(slots)
+
+    # ---- slot-layout pieces (used by Renderer.Render; GetSamples = begin_march + march_rays + materialize) ----------
+    def begin_march(self, rays_o_raw, rays_d_raw, rays_noise=None):
+        """Normalise directions, draw the noise (PersSampler.cu:373-380) and bind the scratch; launches no march yet."""
         rays_o = rays_o_raw.contiguous()
         rays_d = (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
         n_rays = rays_o.shape[0]
-        gdp = self.global_data_pool_
         if rays_noise is None:
             rays_noise = self.make_noise(n_rays, rays_o.device)
-        args = (self.tree_nodes_gpu_, self.pers_trans_gpu_, rays_o, rays_d, rays_noise, self.global_near_, 1e8,
-                self.sample_l_, self.scale_by_dis_, self.max_oct_intersect_per_ray_)
-        scratch = self._scratch(n_rays, rays_o.device)
-        bounds, totals, first = ops.sampler_march(*args, scratch, count_all_hits=self.exact_oct_stat_)
-        n_all_pts, n_all_oct = (int(v) for v in totals.tolist())            # the one sync
+        self._generation = getattr(self, "_generation", 0) + 1
+        return SlotSamples(self, rays_o, rays_d, rays_noise, self._scratch(n_rays, rays_o.device), self._generation)
+
+    def march_rays(self, slots, r0, r1):
+        """March rays [r0, r1) into their slots on the CURRENT stream (no host sync)."""
+        n = r1 - r0
+        if n <= 0:
+            return
+        S = slots.slot
+        totals = torch.empty((2,), dtype=torch.int32, device=slots.rays_o.device)
+        call("f2b_sampler_march", self.tree_nodes_gpu_, self.n_nodes, self.pers_trans_gpu_, self.pers_trans_gpu_.numel() // 544,
+             slots.rays_o[r0:r1], slots.rays_d[r0:r1], slots.noise[r0:], n, float(self.global_near_), 1e8, float(self.sample_l_),
+             int(self.scale_by_dis_), int(self.max_oct_intersect_per_ray_), int(bool(self.exact_oct_stat_)),
+             slots.s_pts[r0 * S:r1 * S], slots.s_dt[r0 * S:r1 * S], slots.s_t[r0 * S:r1 * S], slots.s_anchors[r0 * S:r1 * S],
+             slots.counts[r0:r1], slots.chunk_bounds[r0:r1], totals, slots.first_oct_dis[r0:r1], stream())
+        call("f2b_slot_bounds", slots.counts[r0:r1], n, S, r0, slots.slot_bounds[r0:r1], stream())
+        slots.totals.append(totals)
+
+    def note_totals(self, n_rays, n_all_oct):
+        """EMA of octree intersections per ray (PersSampler.cu:378-379); called once the host knows the totals."""
+        gdp = self.global_data_pool_
         if gdp.mode_ != VALIDATE and n_rays > 0:
             gdp.sampled_oct_per_ray_ = gdp.sampled_oct_per_ray_ * .9 + (n_all_oct / n_rays) * .1
-        pts, dirs, dt, t, anchors = ops.sampler_gather(rays_d, bounds, n_all_pts, scratch)
-        return SampleResultFlex(pts, dirs, dt, t, anchors, bounds, first)
+
+    def materialize(self, slots):
+        """Slot layout -> the reference's SampleResultFlex (cumsum bounds, gathered arrays).  One host sync."""
+        if slots.generation != getattr(self, "_generation", 0):
+            raise RuntimeError("SampleResult: the sampler has marched again; this result's scratch slots were overwritten")
+        R, dev = slots.n_rays, slots.rays_o.device
+        bounds = torch.empty((R, 2), dtype=torch.int32, device=dev)
+        total = torch.zeros((1,), dtype=torch.int32, device=dev)
+        call("f2b_count_scan", slots.counts, R, bounds, total, stream())
+        vals = torch.cat([total] + [t.reshape(-1) for t in slots.totals]).tolist()          # the one sync
+        n_all_pts, n_all_oct = int(vals[0]), int(sum(vals[2::2]))
+        if not getattr(slots, "noted", False):
+            self.note_totals(R, n_all_oct)
+            slots.noted = True
+        pts, dirs, dt, t, anchors = ops.sampler_gather(slots.rays_d, bounds, n_all_pts,
+                                                       (slots.s_pts, slots.s_dt, slots.s_t, slots.s_anchors))
+        return SampleResultFlex(pts, dirs, dt, t, anchors, bounds, slots.first_oct_dis)
 
     def _scratch(self, n_rays, dev):
         """Persistent one-pass march scratch: a 1024-sample slot per ray (28 B/sample), grown on demand."""
@@ -126,17 +202,24 @@ class PersSampler:
 
     def UpdateOctNodes(self, sample_result, sampled_weight, sampled_alpha):
         """PersSampler::UpdateOctNodes (PersSampler.cu:536-603) without the milestone/compaction calls."""
-        n_nodes, n_rays = self.n_nodes, sample_result.pts_idx_bounds.shape[0]
-        dev = self.tree_nodes_gpu_.device
         n_pts = sample_result.anchors.shape[0]
         if sampled_weight.shape[0] != n_pts or sampled_alpha.shape[0] != n_pts:
             raise ValueError("UpdateOctNodes: weight/alpha length must equal the number of samples")
+        self.update_oct_nodes_raw(sample_result.pts_idx_bounds, sample_result.anchors, sampled_weight.contiguous(),
+                                  sampled_alpha.contiguous())
+
+    def update_oct_nodes_raw(self, bounds, anchors, sampled_weight, sampled_alpha):
+        """Same on any sample layout: ``bounds`` [R,2] index rows of ``anchors`` [*, 2 or 3] (node index in column 1)
+        and of the weight / alpha arrays (the renderer passes the march's slot layout)."""
+        n_nodes, n_rays = self.n_nodes, bounds.shape[0]
+        dev = self.tree_nodes_gpu_.device
         vote_w = torch.full((n_nodes,), -1, dtype=torch.int32, device=dev)
         vote_a = torch.full((n_nodes,), -1, dtype=torch.int32, device=dev)
         mark = torch.zeros((n_nodes,), dtype=torch.int32, device=dev)
-        oct_idx = sample_result.anchors.reshape(-1)[1:]                          # anchors[:,1] with stride 3
-        call("f2b_oct_mark_visit", sample_result.pts_idx_bounds, n_rays, oct_idx.data_ptr(), 3,
-             sampled_weight.contiguous(), sampled_alpha.contiguous(), vote_w, vote_a, mark, self.tree_visit_cnt_, stream())
+        stride = anchors.shape[1]
+        oct_idx = anchors.reshape(-1)[1:]                                        # anchors[:,1] with the row stride
+        call("f2b_oct_mark_visit", bounds, n_rays, oct_idx.data_ptr(), stride,
+             sampled_weight, sampled_alpha, vote_w, vote_a, mark, self.tree_visit_cnt_, stream())
         if self.vote_allreduce_ is not None:                                     # DP: identical pruning on every rank
             self.vote_allreduce_(vote_w, vote_a, mark, self.tree_visit_cnt_)
         self.last_votes_ = (vote_w, vote_a, mark)

@@ -150,6 +150,15 @@ int f2b_field_fwd(const void* table_f16, const int* prim_pool, const float* bias
                   int n_pts, int logit_only, float* out_f32, void* feat_save_f16, void* hidden_save_f16,
                   void* stream);
 
+/* The same kernel over the one-pass march's scratch slots: ray r owns slots [r*slot_size, r*slot_size+ray_counts[r])
+ * of slot_pts / slot_vol (slot_size a multiple of 128; tiles past a ray's count are skipped whole).  Outputs use the
+ * same slot indexing.  Lets the early-stop pass of Renderer::Render (Renderer.cpp:107-126) start right behind the
+ * march without the cumsum / host sync / gather that PersSampler::GetSamples performs (PersSampler.cu:395-398). */
+int f2b_field_fwd_slots(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes,
+                        int local_size, const void* mlp_params_f16, const float* slot_pts, const int* slot_vol,
+                        int vol_stride, const int* ray_counts, int n_rays, int slot_size, int logit_only,
+                        float* out_f32, void* feat_save_f16, void* stream);
+
 /* Implementation selection for f2b_mlp_fwd / f2b_mlp_bwd: 1 = tcgen05/TMEM kernels (default when
  * built), 0 = CUDA-core twin (validation).  Env F2B_MLP_IMPL overrides the default. */
 int f2b_set_mlp_impl(int impl);
@@ -208,6 +217,20 @@ int f2b_early_stop(const float* logit, int logit_stride, const float* dt, const 
                    int n_rays, float* weights, float* alphas, uint8_t* keep,
                    int* ray_counts /* [n_rays] caller-owned scratch */,
                    int* new_bounds /* [n_rays,2] */, int* total_kept /* [1] */, void* stream);
+/* The two halves of f2b_early_stop separately (ray-chunked pipelines scan once over all chunks' counts). */
+int f2b_early_stop_rays(const float* logit, int logit_stride, const float* dt, const int* pts_idx_bounds,
+                        int n_rays, float* weights, float* alphas, uint8_t* keep, int* ray_counts, void* stream);
+/* counts[n] -> bounds[n,2] = {exclusive, inclusive} prefix sums, total[0] = sum (torch::cumsum at
+ * PersSampler.cu:395 / FilterIdxBounds, Renderer.cu:8-29). */
+int f2b_count_scan(const int* counts, int n, int* bounds, int* total, void* stream);
+/* slot_bounds[r] = {(first_ray+r)*slot_size, (first_ray+r)*slot_size + ray_counts[r]}: pts_idx_bounds of the scratch layout. */
+int f2b_slot_bounds(const int* ray_counts, int n_rays, int slot_size, int first_ray, int* slot_bounds, void* stream);
+/* f2b_compact_samples reading the march's scratch slots directly (28 B/sample there: pts, dt, t, anchors[0:2]); the
+ * per-sample direction is the ray's (rays_d [n_rays,3], normalised), anchors_o[:,2] = 0. */
+int f2b_compact_slots(const uint8_t* keep, const int* slot_bounds, const int* new_bounds, int n_rays,
+                      const float* rays_d, const float* s_pts, const float* s_dt, const float* s_t,
+                      const int* s_anchors, const void* feat_slots_f16 /* nullable */, float* pts_o, float* dirs_o,
+                      float* dt_o, float* t_o, int* anchors_o, void* feat_o_f16 /* nullable */, void* stream);
 /* Gather-compact the surviving samples (44 B/pt) and, optionally, their encoded features (feat_f16 [P,32]
  * from the early-stop pass -> feat_o_f16 [P',32]) so the gradient pass does not gather the table again. */
 int f2b_compact_samples(const uint8_t* keep, const int* old_bounds, const int* new_bounds, int n_rays,
