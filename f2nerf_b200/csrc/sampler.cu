@@ -297,28 +297,19 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 16-lane variant: one perspective projection per lane (lanes 0..11 of a half-warp; 12..15 idle), two rays per
-// warp => 4x the warps of the 4-lane kernel (the march is latency bound: at 4 lanes/ray 4096 rays are only 512
-// warps on 592 SM sub-partitions) and a 3x shorter instruction stream per step.  The 12-term mixing sums keep
-// the reference's tree: lane 3s+2 forms w*t, lane 3s+1 and 3s fold their term in with one fma each
-// (g_s = fma(w0,t0, fma(w1,t1, w2*t2))), lanes 0 and 6 add their neighbour group (g0+g1, g2+g3), lane 0 adds the
-// halves — 4 shuffles per value, bit-identical to the reference's unrolled redux.  Lane 0 of the half-warp then
-// derives the step and broadcasts it; every lane advances t / walks the octree redundantly (private DFS stack).
+// 16-lane variant: two rays per warp => 4x the warps of the 4-lane kernel (the march is latency bound: at
+// 4 lanes/ray 4096 rays are only 512 warps on 592 SM sub-partitions).  Each step has two phases:
+//   A  lane g < 12 evaluates perspective projection g: xz, 1/xz1, the Jacobian factors T0..T2 and the value V;
+//   B  the 4 x 12 block {T0,T1,T2,V} x projections is transposed through 192 B of shared memory and lane
+//      (r, c) = (g >> 2, g & 3) forms ONE of the 12 mixing sums S[r][c] = sum_i weight[r][i] * T_c[i] serially
+//      in registers, in exactly the reference's order (Eigen's unrolled redux: g_s = fma(w0,t0,fma(w1,t1,w2*t2))
+//      per triple, then (g0+g1)+(g2+g3)) — 15 flops instead of a 4-shuffle tree per sum (r01 profile: the
+//      shuffle trees were 108 of the 366 instructions of a step).
+// The three Jacobian-times-direction rows are then chained over lanes (r,2)->(r,1)->(r,0) with two shuffles, and
+// every lane picks them up (3 shuffles) and derives den / step redundantly, so no broadcast is needed.
+// Every lane advances t / walks the octree redundantly (private DFS stack in shared memory).
 constexpr int kL16 = 16;
 constexpr int kRaysPerBlock16 = 2;
-
-__device__ __forceinline__ float tree12(float w, float tv, int role) {
-  // role = g % 3 for g < 12; returns the full 12-term sum in lane 0 of the half-warp (garbage elsewhere)
-  const float m = fmul(w, tv);
-  const float a1 = __shfl_down_sync(0xffffffffu, m, 1, 16);
-  const float v1 = role == 1 ? ffma(w, tv, a1) : m;
-  const float a2 = __shfl_down_sync(0xffffffffu, v1, 1, 16);
-  const float v0 = ffma(w, tv, a2);                                  // meaningful in lanes 0,3,6,9
-  const float b = __shfl_down_sync(0xffffffffu, v0, 3, 16);
-  const float sg = fadd(v0, b);                                      // lanes 0 and 6
-  const float c = __shfl_down_sync(0xffffffffu, sg, 6, 16);
-  return fadd(sg, c);                                                // lane 0
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(32)
@@ -330,10 +321,13 @@ march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__
                float* __restrict__ o_pts, float* __restrict__ o_dirs, float* __restrict__ o_dt,
                float* __restrict__ o_t, int* __restrict__ o_anchors, float* __restrict__ first_oct_dis) {
   __shared__ int s_stack[32 * kStackPitch];
+  __shared__ __align__(16) float s_T[2][4][12];     // [half-warp][T0,T1,T2,V][projection]
   const int lane = threadIdx.x;
   const int g = lane & 15;                          // lane inside the ray's half-warp
-  const int pi = g < 12 ? g : 11;                   // my projection (idle lanes shadow 11)
-  const int role = g % 3;
+  const int pi = g < 12 ? g : 11;                   // phase A: my projection (idle lanes shadow 11)
+  const int orow = g < 12 ? (g >> 2) : 2;           // phase B: my mixing sum S[orow][ocol]
+  const int ocol = g & 3;
+  float* const tb = &s_T[lane >> 4][0][0];
   int ray = blockIdx.x * kRaysPerBlock16 + (lane >> 4);
   const bool active = ray < n_rays;
   if (!active) ray = n_rays - 1;
@@ -341,6 +335,7 @@ march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__
 
   const float o[3] = {__ldg(rays_o + ray * 3), __ldg(rays_o + ray * 3 + 1), __ldg(rays_o + ray * 3 + 2)};
   const float d[3] = {__ldg(rays_d + ray * 3), __ldg(rays_d + ray * 3 + 1), __ldg(rays_d + ray * 3 + 2)};
+  const float dsel = ocol == 0 ? d[0] : (ocol == 1 ? d[1] : d[2]);
   const float* noise = rays_noise + ray;
   Dfs dfs;
   dfs.stack = s_stack + lane * kStackPitch;
@@ -362,7 +357,10 @@ march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__
   float t = hit.near, far = hit.far;
   int cur_node = hit.node, cur_trans = hit.trans_idx, loaded_trans = -1;
   bool first = true;
-  float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 1.f}, pw[3] = {0.f, 0.f, 0.f};
+  float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 1.f};
+  float wr[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) wr[i] = 0.f;
   float rclip = 1.f;
   bool running = have && cap > 0;
   while (__any_sync(0xffffffffu, running)) {
@@ -372,13 +370,16 @@ march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__
       const float4 rb = __ldg(reinterpret_cast<const float4*>(&T->w2xz[pi][4]));
       pa[0] = ra.x; pa[1] = ra.y; pa[2] = ra.z; pa[3] = ra.w;
       pb[0] = rb.x; pb[1] = rb.y; pb[2] = rb.z; pb[3] = rb.w;
-#pragma unroll
-      for (int r = 0; r < 3; r++) pw[r] = __ldg(&T->weight[r][pi]);
+      const float4* wp = reinterpret_cast<const float4*>(&T->weight[orow][0]);
+      const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+      wr[0] = w0.x; wr[1] = w0.y; wr[2] = w0.z; wr[3] = w0.w; wr[4] = w1.x; wr[5] = w1.y; wr[6] = w1.z; wr[7] = w1.w;
+      wr[8] = w2.x; wr[9] = w2.y; wr[10] = w2.z; wr[11] = w2.w;
       const float4 cd = __ldg(reinterpret_cast<const float4*>(&T->center[0]));
       const float ex = fsub(o[0], cd.x), ey = fsub(o[1], cd.y), ez = fsub(o[2], cd.z);
       rclip = fmaxf(fdiv(fsqrt(ffma(ex, ex, ffma(ey, ey, fmul(ez, ez)))), cd.w), 1.f);
       loaded_trans = cur_trans;
     }
+    // ---- phase A: my projection -------------------------------------------------------------------
     const float X = ffma(t, d[0], o[0]), Y = ffma(t, d[1], o[1]), Z = ffma(t, d[2], o[2]);
     const float xz0 = fadd(ffma(X, pa[0], fmul(Y, pa[1])), ffma(Z, pa[2], pa[3]));
     const float xz1 = fadd(ffma(X, pb[0], fmul(Y, pb[1])), ffma(Z, pb[2], pb[3]));
@@ -387,39 +388,44 @@ march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__
     const float T0 = ffma(pa[0], rr, fmul(pb[0], q));
     const float T1 = ffma(rr, pa[1], fmul(q, pb[1]));
     const float T2 = ffma(rr, pa[2], fmul(q, pb[2]));
-    float proj[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      const float j0 = tree12(pw[r], T0, role), j1 = tree12(pw[r], T1, role), j2 = tree12(pw[r], T2, role);
-      proj[r] = ffma(j0, d[0], ffma(j1, d[1], fmul(j2, d[2])));
+    if (g < 12) {
+      tb[g] = T0; tb[12 + g] = T1; tb[24 + g] = T2;
+      if (FILL) tb[36 + g] = fdiv(xz0, xz1);
     }
-    float w[3] = {0.f, 0.f, 0.f};
-    if (FILL) {
-      const float V = fdiv(xz0, xz1);
-#pragma unroll
-      for (int r = 0; r < 3; r++) w[r] = tree12(pw[r], V, role);
-    }
-    // leader (lane 0 of the half-warp) holds the true sums; everybody computes, the leader's values are broadcast
-    float den = fadd(fsqrt(ffma(proj[0], proj[0], ffma(proj[1], proj[1], fmul(proj[2], proj[2])))), 1e-6f);
+    __syncwarp();
+    // ---- phase B: my mixing sum, serial in the reference's order ------------------------------------
+    const float4* tv = reinterpret_cast<const float4*>(tb + ocol * 12);
+    const float4 ta = tv[0], tc = tv[1], te = tv[2];
+    __syncwarp();                                              // the block may be overwritten by the next step
+    const float g0 = ffma(wr[0], ta.x, ffma(wr[1], ta.y, fmul(wr[2], ta.z)));
+    const float g1 = ffma(wr[3], ta.w, ffma(wr[4], tc.x, fmul(wr[5], tc.y)));
+    const float g2 = ffma(wr[6], tc.z, ffma(wr[7], tc.w, fmul(wr[8], te.x)));
+    const float g3 = ffma(wr[9], te.y, ffma(wr[10], te.z, fmul(wr[11], te.w)));
+    const float Sv = fadd(fadd(g0, g1), fadd(g2, g3));         // S[orow][ocol]
+    // proj[r] = fma(j0,d0, fma(j1,d1, j2*d2)) chained over lanes (r,2) -> (r,1) -> (r,0)
+    const float m2 = fmul(Sv, dsel);
+    const float v1 = ffma(Sv, dsel, __shfl_down_sync(0xffffffffu, m2, 1, 16));
+    const float pj = ffma(Sv, dsel, __shfl_down_sync(0xffffffffu, v1, 1, 16));          // meaningful in lanes 0, 4, 8
+    const float p0 = __shfl_sync(0xffffffffu, pj, 0, 16), p1 = __shfl_sync(0xffffffffu, pj, 4, 16),
+                p2 = __shfl_sync(0xffffffffu, pj, 8, 16);
+    const float den = fadd(fsqrt(ffma(p0, p0, ffma(p1, p1, fmul(p2, p2)))), 1e-6f);
     float step = fdiv(fmul(sample_l, __ldg(noise + k)), den);
     if (scale_by_dis) step = fmul(rclip, step);
-    den = __shfl_sync(0xffffffffu, den, 0, 16);
-    step = __shfl_sync(0xffffffffu, step, 0, 16);
 
     if (running) {
       if (!first) {
         if (FILL && active) {
           const size_t idx = out_base + k;
-          if (g == 0) {
-            o_pts[idx * 3] = w[0]; o_pts[idx * 3 + 1] = w[1]; o_pts[idx * 3 + 2] = w[2];
-          } else if (g == 1) {
-            if (MODE == 1) { o_dirs[idx * 3] = d[0]; o_dirs[idx * 3 + 1] = d[1]; o_dirs[idx * 3 + 2] = d[2]; }
-          } else if (g == 2) {
+          if (ocol == 3 && g < 12) {
+            o_pts[idx * 3 + orow] = Sv;                          // the warped point: S[0..2][3] live in lanes 3, 7, 11
+          } else if (g == 0) {
             o_dt[idx] = fmul(step, den);
             o_t[idx] = t;
-          } else if (g == 3) {
+          } else if (g == 1) {
             if (MODE == 1) { o_anchors[idx * 3] = cur_trans; o_anchors[idx * 3 + 1] = cur_node; o_anchors[idx * 3 + 2] = 0; }
             else { o_anchors[idx * 2] = cur_trans; o_anchors[idx * 2 + 1] = cur_node; }
+          } else if (g == 2) {
+            if (MODE == 1) { o_dirs[idx * 3] = d[0]; o_dirs[idx * 3 + 1] = d[1]; o_dirs[idx * 3 + 2] = d[2]; }
           }
         }
         k++;
