@@ -123,10 +123,31 @@ def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None):
 
 
 ALGO_BYTES = {  # algorithmic bytes per unit (sample) at the operator boundary — DESIGN.md "roofline accounting"
-    "f2b_field_fwd": 16 + 512 + 64, "f2b_hash_fwd": 16 + 512 + 64, "f2b_hash_bwd": 16 + 64 + 512, "f2b_sampler_fill": 44, "f2b_sampler_count": 0,
+    "f2b_field_fwd": 16 + 512 + 64, "f2b_field_fwd_slots": 16 + 512 + 64, "f2b_sampler_march": 28, "f2b_compact_slots": 28 + 64 + 44 + 64,
+    "f2b_hash_fwd": 16 + 512 + 64, "f2b_hash_bwd": 16 + 64 + 512, "f2b_sampler_fill": 44, "f2b_sampler_count": 0,
     "f2b_composite_fwd": 28, "f2b_composite_bwd": 24 + 16 + 16, "f2b_early_stop": 8 + 9, "f2b_compact_samples": 88,
     "f2b_shader_prep": 64 + 12 + 64, "f2b_shader_act": 32 + 12, "f2b_cast_f16_to_f32": 6, "f2b_cast_f32_to_f16": 6,
 }
+
+
+NCU_KERNEL = {"f2b_hash_bwd": "hash_bwd_kernel<1>", "f2b_sampler_march": "march16_kernel<2>",
+              "f2b_field_fwd_slots": "field_fwd_kernel<1, 4>", "f2b_field_fwd": "field_fwd_kernel<1, 4>",
+              "f2b_compact_slots": "compact_slots_kernel", "f2b_composite_fwd": "composite_fwd_kernel",
+              "f2b_composite_bwd": "composite_bwd_kernel"}
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind C-ABI call ``name``, from the
+    committed `ncu --set full` capture of this same command (profiles/*_traffic.json, newest round); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files or name not in NCU_KERNEL:
+        return None
+    try:
+        k = json.load(open(files[-1]))["kernels"].get(NCU_KERNEL[name])
+        return None if k is None else {"dram_bytes_per_launch": k["dram_bytes_per_launch"], "source": os.path.basename(files[-1])}
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def unit_count(name, ints):
@@ -249,7 +270,7 @@ def run_ours(args):
         units = rec["units"] / rec["calls"] if rec["units"] else n_samples / args.steps / max(world, 1)
         byts = ALGO_BYTES.get(name, 0) * units
         roof = dict(bound="hbm", achieved=byts / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=name, ms_per_launch=per_launch_ms,
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(name), kernel=name, ms_per_launch=per_launch_ms,
                 share_of_step=rec["ms"] / max(total_traced, 1e-9), peak_source=peaks["src"])
     rays_total = args.rays * world * args.steps
     line = {

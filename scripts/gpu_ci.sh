@@ -16,6 +16,7 @@ if [ "${SANITIZE:-0}" = "1" ]; then
   F2B_MLP_IMPL=$IMPL timeout 900 compute-sanitizer --tool memcheck --print-limit 8 python -m pytest "tests/test_gpu_render.py::test_render_train_step_matches_oracle" -q -x -p no:cacheprovider -k "64" > gpurun_out/sanitizer.log 2>&1
   grep -E "Invalid|at 0x|by thread|Address|in /|\.cu:|=========     at|ERROR SUMMARY" gpurun_out/sanitizer.log | head -40
 fi
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -n 2
 F2B_MLP_IMPL=$IMPL timeout 500 python bench.py --steps ${STEPS:-5} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 du -sh gpurun_out
