@@ -98,6 +98,9 @@ public:
     Tensor feat16 = torch::empty({n, 32}, CUDAHalf), out16 = torch::empty({n, 16}, CUDAHalf), hidden = torch::empty({1, n, 64}, CUDAHalf);
     F2B_CHECK(f2b_hash_fwd(table16.data_ptr(), f->prim_pool_.data_ptr<int>(), f->bias_pool_.data_ptr<float>(), f->n_volumes_,
                            local_size, points.data_ptr<float>(), anchors.data_ptr<int>(), 1, n, feat16.data_ptr(), cur_stream()));
+    // RNG-stream parity: the reference allocates the MLP output with torch::rand (TCNNWP.cpp:143), which the draws
+    // that follow (edge samples, next iteration's noise) depend on.  Same call, result discarded.
+    (void)torch::rand({(n + 127) / 128 * 128, 16}, CUDAHalf);
     F2B_CHECK(f2b_mlp_fwd(feat16.data_ptr(), params16.data_ptr(), 0, n, out16.data_ptr(), hidden.data_ptr(), cur_stream()));
     Tensor out = torch::empty({n, 16}, CUDAFloat);
     F2B_CHECK(f2b_cast_f16_to_f32(out16.data_ptr(), out.data_ptr<float>(), out.numel(), 1.f, cur_stream()));
@@ -149,6 +152,7 @@ public:
     Tensor x = torch::cat({feats, sh}, -1).contiguous(), x16 = torch::empty({n, 32}, CUDAHalf);
     F2B_CHECK(f2b_cast_f32_to_f16(x.data_ptr<float>(), x16.data_ptr(), x.numel(), 1.f, cur_stream()));
     Tensor raw = torch::empty({n, 16}, CUDAHalf), hidden = torch::empty({2, n, 64}, CUDAHalf), rgb = torch::empty({n, 3}, CUDAFloat);
+    (void)torch::rand({(n + 127) / 128 * 128, 16}, CUDAHalf);      // RNG-stream parity (TCNNWP.cpp:143), see FieldFn
     F2B_CHECK(f2b_mlp_fwd(x16.data_ptr(), params16.data_ptr(), 1, n, raw.data_ptr(), hidden.data_ptr(), cur_stream()));
     F2B_CHECK(f2b_shader_act(raw.data_ptr(), n, rgb.data_ptr<float>(), cur_stream()));
     ctx->save_for_backward({params16, x16, hidden, raw});
