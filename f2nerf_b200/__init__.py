@@ -8,9 +8,10 @@ this package is the thin host-side mirror of the reference's operator surface
 from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missing)
 from .field import Hash3DAnchored, TCNNWP
 from .ops import CustomOps, FlexOps
+from .optim import FusedAdam
 from .renderer import Renderer, RenderResult, check_backward_nan
 from .sampler import TRAIN, VALIDATE, GlobalDataPool, PersSampler, SampleResultFlex
 from .shader import SHShader
 
-__all__ = ["Hash3DAnchored", "TCNNWP", "CustomOps", "FlexOps", "Renderer", "RenderResult", "check_backward_nan",
+__all__ = ["FusedAdam", "Hash3DAnchored", "TCNNWP", "CustomOps", "FlexOps", "Renderer", "RenderResult", "check_backward_nan",
            "TRAIN", "VALIDATE", "GlobalDataPool", "PersSampler", "SampleResultFlex", "SHShader"]

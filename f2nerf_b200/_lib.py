@@ -51,6 +51,7 @@ SIGNATURES = {
     "f2b_mlp_fwd": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_f32": [_P, _P, c_int, c_int, _P, _P, _P, _P],
     "f2b_mlp_bwd": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_mlp_bwd2": [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_v0": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_bwd_v0": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_tc": [_P, _P, c_int, c_int, _P, _P, _P],
@@ -68,6 +69,8 @@ SIGNATURES = {
     "f2b_shader_act_bwd": [_P, _P, c_int, c_float, _P, _P],
     "f2b_shader_prep_bwd": [_P, _P, _P, c_int, c_float, _P, _P, _P],
     "f2b_shader_prep_bwd_f16": [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P],
+    "f2b_adam_step": [_P, _P, _P, _P, c_i64, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                      ctypes.c_double, c_i64, _P, _P],
     "f2b_early_stop": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P],
     "f2b_early_stop_rays": [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "f2b_count_scan": [_P, c_int, _P, _P, _P],

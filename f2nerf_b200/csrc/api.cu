@@ -10,9 +10,11 @@
 
 extern "C" int f2b_mlp_fwd_v0(const void*, const void*, int, int, void*, void*, void*);
 extern "C" int f2b_mlp_bwd_v0(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
+extern "C" int f2b_mlp_bwd2_v0(const void*, const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
 #ifdef F2B_HAVE_TC
 extern "C" int f2b_mlp_fwd_tc(const void*, const void*, int, int, void*, void*, void*);
 extern "C" int f2b_mlp_bwd_tc(const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
+extern "C" int f2b_mlp_bwd2_tc(const void*, const void*, const void*, const void*, const void*, int, int, void*, float*, void*);
 extern "C" int f2b_mlp_fwd_tc_f32(const void*, const void*, int, int, float*, void*, void*, void*);
 #endif
 extern "C" int f2b_cast_f16_to_f32(const void* src, float* dst, int64_t n, float scale, void* stream);
@@ -79,4 +81,15 @@ extern "C" int f2b_mlp_bwd(const void* dout_f16, const void* in_f16, const void*
   if (mlp_bwd_impl() == 1) return f2b_mlp_bwd_tc(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 #endif
   return f2b_mlp_bwd_v0(dout_f16, in_f16, hidden_save_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
+}
+
+// Backward with the per-layer activation blocks passed separately (row ranges of a larger saved batch:
+// ray-chunked backward passes on separate streams).  dparams is ACCUMULATED into (caller zeroes once).
+extern "C" int f2b_mlp_bwd2(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,
+                            const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                            float* dparams_f32, void* stream) {
+#ifdef F2B_HAVE_TC
+  if (mlp_bwd_impl() == 1) return f2b_mlp_bwd2_tc(dout_f16, in_f16, hidden0_f16, hidden1_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
+#endif
+  return f2b_mlp_bwd2_v0(dout_f16, in_f16, hidden0_f16, hidden1_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 }

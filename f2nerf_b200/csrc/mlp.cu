@@ -131,8 +131,8 @@ mlp_fwd_v0_kernel(const __half* __restrict__ in, const __half* __restrict__ para
 template <int NH>
 __global__ void __launch_bounds__(kTile)
 mlp_bwd_v0_kernel(const __half* __restrict__ dout, const __half* __restrict__ in,
-                  const __half* __restrict__ hidden, const __half* __restrict__ params, int n_pts,
-                  __half* __restrict__ din, float* __restrict__ dparams) {
+                  const __half* __restrict__ hidden, const __half* __restrict__ hid_last,
+                  const __half* __restrict__ params, int n_pts, __half* __restrict__ din, float* __restrict__ dparams) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // transposed fp32 weights so the backward products read rows:  WoT [64][16], WhT [64][64], W0T [32][64]
   float* WoT = reinterpret_cast<float*>(smem_raw);
@@ -165,7 +165,6 @@ mlp_bwd_v0_kernel(const __half* __restrict__ dout, const __half* __restrict__ in
   __syncthreads();
 
   const int n_tiles = (n_pts + kTile - 1) / kTile;
-  const __half* hid_last = hidden + size_t(NH) * n_pts * kW;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTile + t;
     const bool valid = p < n_pts;
@@ -329,12 +328,12 @@ extern "C" int f2b_mlp_fwd_v0(const void* in_f16, const void* params_f16, int n_
   return check_launch("f2b_mlp_fwd");
 }
 
-extern "C" int f2b_mlp_bwd_v0(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
-                              const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
-                              float* dparams_f32, void* stream) {
+extern "C" int f2b_mlp_bwd2_v0(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,
+                               const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                               float* dparams_f32, void* stream) {
   if (n_pts <= 0) return F2B_OK;
-  F2B_REQUIRE(dout_f16 && in_f16 && hidden_save_f16 && params_f16 && dparams_f32, "f2b_mlp_bwd: null pointer");
-  F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_bwd: n_hidden_matmuls must be 0 or 1");
+  F2B_REQUIRE(dout_f16 && in_f16 && hidden0_f16 && params_f16 && dparams_f32, "f2b_mlp_bwd: null pointer");
+  F2B_REQUIRE(n_hidden_matmuls == 0 || (n_hidden_matmuls == 1 && hidden1_f16), "f2b_mlp_bwd: n_hidden_matmuls must be 0 or 1 (with hidden1)");
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   const int n_tiles = div_up(n_pts, kTile);
@@ -343,13 +342,23 @@ extern "C" int f2b_mlp_bwd_v0(const void* dout_f16, const void* in_f16, const vo
   if (n_hidden_matmuls == 0) {
     cudaFuncSetAttribute(mlp_bwd_v0_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mlp_bwd_v0_kernel<0><<<grid, kTile, smem, as_stream(stream)>>>((const __half*)dout_f16, (const __half*)in_f16,
-                                                                 (const __half*)hidden_save_f16, (const __half*)params_f16,
-                                                                 n_pts, (__half*)din_f16, dparams_f32);
+                                                                 (const __half*)hidden0_f16, (const __half*)hidden0_f16,
+                                                                 (const __half*)params_f16, n_pts, (__half*)din_f16, dparams_f32);
   } else {
     cudaFuncSetAttribute(mlp_bwd_v0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mlp_bwd_v0_kernel<1><<<grid, kTile, smem, as_stream(stream)>>>((const __half*)dout_f16, (const __half*)in_f16,
-                                                                 (const __half*)hidden_save_f16, (const __half*)params_f16,
-                                                                 n_pts, (__half*)din_f16, dparams_f32);
+                                                                 (const __half*)hidden0_f16, (const __half*)hidden1_f16,
+                                                                 (const __half*)params_f16, n_pts, (__half*)din_f16, dparams_f32);
   }
   return check_launch("f2b_mlp_bwd");
+}
+
+extern "C" int f2b_mlp_bwd_v0(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                              const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                              float* dparams_f32, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(hidden_save_f16, "f2b_mlp_bwd: null pointer");
+  const __half* h = (const __half*)hidden_save_f16;
+  return f2b_mlp_bwd2_v0(dout_f16, in_f16, h, h + size_t(n_hidden_matmuls ? 1 : 0) * n_pts * kW, params_f16, n_hidden_matmuls, n_pts,
+                         din_f16, dparams_f32, stream);
 }

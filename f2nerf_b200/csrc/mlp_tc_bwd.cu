@@ -122,7 +122,8 @@ __device__ __forceinline__ void relu_bwd_epilogue(uint32_t tmem_row, const unsig
 template <int NH>
 __global__ void __launch_bounds__(kBT)
 mlp_bwd_tc_kernel(const __half* __restrict__ dout, const __half* __restrict__ in, const __half* __restrict__ hidden,
-                  const __half* __restrict__ params, int n_pts, __half* __restrict__ din, float* __restrict__ dparams) {
+                  const __half* __restrict__ hid_last, const __half* __restrict__ params, int n_pts,
+                  __half* __restrict__ din, float* __restrict__ dparams) {
   using S = BwdSmem<NH>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -130,7 +131,6 @@ mlp_bwd_tc_kernel(const __half* __restrict__ dout, const __half* __restrict__ in
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (n_pts + kBT - 1) / kBT;
-  const __half* hid_last = hidden + size_t(NH) * n_pts * 64;
   const uint32_t stage0 = smem_u32(sm + S::STAGE0);
 
   int tile = blockIdx.x;
@@ -284,12 +284,12 @@ mlp_bwd_tc_kernel(const __half* __restrict__ dout, const __half* __restrict__ in
 
 using namespace f2b;
 
-extern "C" int f2b_mlp_bwd_tc(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
-                              const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
-                              float* dparams_f32, void* stream) {
+extern "C" int f2b_mlp_bwd2_tc(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,
+                               const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                               float* dparams_f32, void* stream) {
   if (n_pts <= 0) return F2B_OK;
-  F2B_REQUIRE(dout_f16 && in_f16 && hidden_save_f16 && params_f16 && dparams_f32, "f2b_mlp_bwd: null pointer");
-  F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_bwd: n_hidden_matmuls must be 0 or 1");
+  F2B_REQUIRE(dout_f16 && in_f16 && hidden0_f16 && params_f16 && dparams_f32, "f2b_mlp_bwd: null pointer");
+  F2B_REQUIRE(n_hidden_matmuls == 0 || (n_hidden_matmuls == 1 && hidden1_f16), "f2b_mlp_bwd: n_hidden_matmuls must be 0 or 1 (with hidden1)");
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   const int n_tiles = div_up(n_pts, kBT);
@@ -297,14 +297,24 @@ extern "C" int f2b_mlp_bwd_tc(const void* dout_f16, const void* in_f16, const vo
     const int grid = n_tiles < sms * 3 ? n_tiles : sms * 3;
     cudaFuncSetAttribute(mlp_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<0>::BYTES);
     mlp_bwd_tc_kernel<0><<<grid, kBT, BwdSmem<0>::BYTES, as_stream(stream)>>>(
-        (const __half*)dout_f16, (const __half*)in_f16, (const __half*)hidden_save_f16, (const __half*)params_f16, n_pts,
-        (__half*)din_f16, dparams_f32);
+        (const __half*)dout_f16, (const __half*)in_f16, (const __half*)hidden0_f16, (const __half*)hidden0_f16,
+        (const __half*)params_f16, n_pts, (__half*)din_f16, dparams_f32);
   } else {
     const int grid = n_tiles < sms * 2 ? n_tiles : sms * 2;
     cudaFuncSetAttribute(mlp_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<1>::BYTES);
     mlp_bwd_tc_kernel<1><<<grid, kBT, BwdSmem<1>::BYTES, as_stream(stream)>>>(
-        (const __half*)dout_f16, (const __half*)in_f16, (const __half*)hidden_save_f16, (const __half*)params_f16, n_pts,
-        (__half*)din_f16, dparams_f32);
+        (const __half*)dout_f16, (const __half*)in_f16, (const __half*)hidden0_f16, (const __half*)hidden1_f16,
+        (const __half*)params_f16, n_pts, (__half*)din_f16, dparams_f32);
   }
   return check_launch("f2b_mlp_bwd(tcgen05)");
+}
+
+extern "C" int f2b_mlp_bwd_tc(const void* dout_f16, const void* in_f16, const void* hidden_save_f16,
+                              const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16,
+                              float* dparams_f32, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(hidden_save_f16, "f2b_mlp_bwd: null pointer");
+  const __half* h = (const __half*)hidden_save_f16;
+  return f2b_mlp_bwd2_tc(dout_f16, in_f16, h, h + size_t(n_hidden_matmuls ? 1 : 0) * n_pts * 64, params_f16, n_hidden_matmuls, n_pts,
+                         din_f16, dparams_f32, stream);
 }

@@ -146,9 +146,36 @@ class Hash3DAnchored:
         self.local_size_ = ((self.pool_size_ // N_LEVELS) >> 4) << 4        # Hash3DAnchored.cpp:73-75
         self.mlp_ = TCNNWP(global_data_pool, N_LEVELS * N_CHANNELS, mlp_out_dim, mlp_hidden_dim, n_hidden_layers, device)
 
+    n_levels_ = N_LEVELS
+
     def table_f16(self):
-        """fp16 shadow of the master table (the reference re-casts on every call, Hash3DAnchored.cu:186)."""
-        return ops.table_to_half(self.feat_pool_.detach())
+        """fp16 shadow of the master table.  The reference re-casts all 64 MB on every call (Hash3DAnchored.cu:186);
+        here the shadow is cached and reused while the master is unchanged: torch-side writes bump the tensor's
+        version counter (-> re-cast), FusedAdam refreshes the shadow itself in the same kernel that updates the master."""
+        if not getattr(self, "_shadow_managed_", False):          # default: like the reference, always from the master
+            return ops.table_to_half(self.feat_pool_.detach())
+        ver = self.feat_pool_._version
+        sh = getattr(self, "_shadow_", None)
+        if sh is None or self._shadow_ver_ != ver or sh.device != self.feat_pool_.device:
+            sh = self._shadow_ = ops.table_to_half(self.feat_pool_.detach())
+            self._shadow_ver_ = ver
+        return sh
+
+    def manage_shadow(self, on=True):
+        """Opt in to the cached shadow (FusedAdam does).  While on, the master must only change through FusedAdam,
+        ``Reset``/``LoadStates`` or version-tracked torch in-place ops (writes through ``.data`` are invisible to the cache)."""
+        self._shadow_managed_ = bool(on)
+        self._shadow_ = None
+
+    def invalidate_shadow(self):
+        self._shadow_ = None
+
+    def shadow_for_update(self):
+        """The fp16 shadow buffer a fused optimizer step writes next to the master (fully initialised first)."""
+        return self.table_f16()
+
+    def shadow_updated(self):
+        self._shadow_ver_ = self.feat_pool_._version
 
     def AnchoredQuery(self, points, anchors):
         """Hash3DAnchored::AnchoredQuery (Hash3DAnchored.cpp:84-99): [n,3] warped points + [n] trans_idx
@@ -161,6 +188,7 @@ class Hash3DAnchored:
 
     def LoadStates(self, states, idx):
         self.feat_pool_.data.copy_(states[idx]); idx += 1
+        self.invalidate_shadow()
         self.prim_pool_ = states[idx].clone().to(self.feat_pool_.device).contiguous(); idx += 1
         self.bias_pool_.data.copy_(states[idx]); idx += 1
         self.n_volumes_ = int(states[idx].item()); idx += 1
@@ -174,6 +202,7 @@ class Hash3DAnchored:
 
     def Reset(self):
         self.feat_pool_.data.uniform_(-1e-2, 1e-2)
+        self.invalidate_shadow()
         self.mlp_.InitParams()
 
 

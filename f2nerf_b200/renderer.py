@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from ._lib import call, stream
 from .field import field_backward, field_forward, field_forward_from_features
 from .rng import burn_mlp_output, burn_rand
 from .sampler import TRAIN, VALIDATE, LazySampleResult, SampleResultFlex
@@ -99,8 +100,15 @@ class Renderer:
             for st in lanes[1:]:
                 main.wait_stream(st)
             new_bounds, total = ops.count_scan(kept_counts, n_rays)
-            vals = torch.cat([total] + [t.reshape(-1) for t in slots.totals]).tolist()   # THE host sync of the step
-            n_kept, n_all, n_all_oct = int(vals[0]), int(sum(vals[1::2])), int(sum(vals[2::2]))
+            cut_rays = self._bwd_cut_rays(n_rays)                    # interior ray boundaries of the backward's chunks
+            head = [total] + ([new_bounds[cut_rays, 0]] if cut_rays is not None else [])
+            n_head = 1 + (0 if cut_rays is None else cut_rays.numel())
+            vals = torch.cat(head + [t.reshape(-1) for t in slots.totals]).tolist()      # THE host sync of the step
+            n_kept = int(vals[0])
+            n_all, n_all_oct = int(sum(vals[n_head::2])), int(sum(vals[n_head + 1::2]))
+            rcut = [0] + ([] if cut_rays is None else self._cut_list) + [n_rays]
+            scut = [0] + [int(v) for v in vals[1:n_head]] + [n_kept]
+            self._bwd_cuts_ = [(rcut[i], rcut[i + 1], scut[i], scut[i + 1]) for i in range(len(rcut) - 1)]
             sampler.note_totals(n_rays, n_all_oct)
             slots.noted = True
             self.n_sampled_pts_, self.n_kept_pts_ = n_all, n_kept     # host-side counts of this call (no extra sync)
@@ -173,6 +181,22 @@ class Renderer:
             t = pool[name] = torch.empty((max(n, 1),), dtype=dtype, device=dev)
         return t[:n].view(*shape)
 
+    def _bwd_cut_rays(self, n_rays):
+        """Device index tensor of the interior ray boundaries of the backward chunks (F2B_BWD_CHUNKS / ``bwd_chunks_``)."""
+        if not hasattr(self, "bwd_chunks_"):
+            self.bwd_chunks_ = int(os.environ.get("F2B_BWD_CHUNKS", "1"))
+        k = max(1, min(int(self.bwd_chunks_), 16, (n_rays + 255) // 256))
+        if k <= 1:
+            self._cut_list = []
+            return None
+        key = (n_rays, k)
+        if getattr(self, "_cut_key", None) != key:
+            step = -(-n_rays // k)
+            self._cut_list = [r for r in range(step, n_rays, step)]
+            self._cut_dev = torch.tensor(self._cut_list, dtype=torch.int64, device=self.app_emb_.device) if self._cut_list else None
+            self._cut_key = key
+        return self._cut_dev
+
     def _ray_chunks(self, n_rays):
         """Ray ranges marched on separate streams (F2B_RAY_CHUNKS / ``ray_chunks_``; 1 = single stream)."""
         if not hasattr(self, "ray_chunks_"):
@@ -222,6 +246,7 @@ class _RenderFunction(torch.autograd.Function):
         colors, disparity, depth, weights = ops.composite_fwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg)
         edge_feats = scene_feat[n_kept:].reshape(-1, 2, 16)
         ctx.renderer, ctx.es, ctx.n_kept = renderer, es, n_kept
+        ctx.cuts = renderer._bwd_cuts_ if getattr(renderer, "_bwd_cuts_", None) else [(0, es.pts_idx_bounds.shape[0], 0, n_kept)]
         ctx.pack = (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
                     s_hidden, rgb)
         ctx.gs_progress = renderer.global_data_pool_.gradient_scaling_progress_
@@ -249,26 +274,61 @@ class _RenderFunction(torch.autograd.Function):
         if ctx.gs_progress < 1.:                          # GradientScaling::backward draws an unused rand_like (CustomOps.cu:154)
             burn_rand(n_kept * 3, dev)
             burn_rand(n_kept, dev)
-        # composite (+TruncExp, +GradientScaling) -> d logit, d rgb
-        d_logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
-        d_rgb = ops.composite_bwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg, d_colors, d_disp, d_depth,
-                                  d_weights, ctx.gs_progress, d_logit, 1)
-        # shader: sigmoid -> MLP -> input assembly; the last kernel writes the field MLP's fp16 dL/dout directly
+        # ---- backward, optionally in ray chunks (bwd_chunks_ / F2B_BWD_CHUNKS): the dense chain (composite -> sigmoid ->
+        # shader MLP -> input assembly -> field MLP; HBM streaming) of chunk k+1 on the main stream, the hash scatter of
+        # chunk k (L2 reductions) on a side stream.  Measured on B200 (r01): co-running them is SLOWER (6.05 ms at 1
+        # chunk, 6.5 / 6.8 / 7.7 ms at 2 / 4 / 8: the scatter's 260 k small blocks crowd out the persistent tcgen05 CTAs),
+        # so the default is one chunk; the scatter still runs on the side stream behind an event.
         s_scale, f_scale = shader.mlp_.loss_scale_, field.mlp_.loss_scale_
-        d_raw = ops.shader_act_bwd(raw, d_rgb, s_scale)
-        d_in16, d_sparams = ops.mlp_bwd(d_raw, mlp_in, s_hidden, sparams16, shader.mlp_.n_hidden_matmuls, need_din=True)
-        d_sparams = d_sparams / s_scale
+        nh_s, nh_f = shader.mlp_.n_hidden_matmuls, field.mlp_.n_hidden_matmuls
+        f16 = lambda *sh: torch.empty(sh, dtype=torch.float16, device=dev)
+        d_logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((n_kept, 3), dtype=torch.float32, device=dev)
+        d_raw, d_in16, d_scene16, dfeat16 = f16(n_kept, 16), f16(n_kept, 32), f16(n_q, 16), f16(n_q, 32)
+        d_sparams, d_fparams = zeros(sparams16.numel()), zeros(fparams16.numel())
+        d_table = torch.zeros_like(field.feat_pool_)
         d_app = torch.zeros_like(renderer.app_emb_) if ray_emb_idx is not None else None
-        d_scene16 = torch.empty((n_q, 16), dtype=torch.float16, device=dev)
         if n_q > n_kept:
             if d_edge is not None:
                 d_scene16[n_kept:] = (d_edge.reshape(-1, 16) * f_scale).to(torch.float16)
             else:
                 d_scene16[n_kept:].zero_()
-        ops.shader_prep_bwd_f16(d_in16, d_logit, es.pts_idx_bounds, ray_emb_idx, 1.0 / s_scale, f_scale, d_scene16, d_app)
-        # field: MLP -> hash scatter
-        d_table, d_fparams = field_backward(field, fparams16, None, None, 1, feat16, f_hidden, None, d_out_f16=d_scene16,
-                                            segments=segments)
+        main = torch.cuda.current_stream(dev)
+        side = renderer._side_stream(dev, 2)
+        bounds = es.pts_idx_bounds
+        hash_args = (field.prim_pool_, field.bias_pool_, int(field.n_volumes_), int(field.local_size_))
+
+        def scatter(pts, anc, stride, s0, s1):            # on the side stream, behind everything queued on main so far
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                ops.hash_bwd(*hash_args, pts, anc, stride, dfeat16[s0:s1], 1.0 / f_scale, d_table)
+
+        for r0, r1, s0, s1 in ctx.cuts:
+            if s1 <= s0:
+                continue
+            nr, ns = r1 - r0, s1 - s0
+            call("f2b_composite_bwd", scene_feat, 16, rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr, d_colors[r0:r1],
+                 None if d_disp is None else d_disp[r0:r1], None if d_depth is None else d_depth[r0:r1], d_weights,
+                 float(ctx.gs_progress), d_logit, 1, d_rgb, stream())
+            call("f2b_shader_act_bwd", raw[s0:s1], d_rgb[s0:s1], ns, float(s_scale), d_raw[s0:s1], stream())
+            call("f2b_mlp_bwd2", d_raw[s0:s1], mlp_in[s0:s1], s_hidden[0, s0:s1], s_hidden[1, s0:s1] if nh_s else None,
+                 sparams16, int(nh_s), ns, d_in16[s0:s1], d_sparams, stream())
+            ops.shader_prep_bwd_f16(d_in16, d_logit, bounds[r0:r1], None if ray_emb_idx is None else ray_emb_idx[r0:r1],
+                                    1.0 / s_scale, f_scale, d_scene16, d_app)
+            call("f2b_mlp_bwd2", d_scene16[s0:s1], feat16[s0:s1], f_hidden[0, s0:s1], f_hidden[1, s0:s1] if nh_f else None,
+                 fparams16, int(nh_f), ns, dfeat16[s0:s1], d_fparams, stream())
+            scatter(segments[0][0][s0:s1], segments[0][1][s0:s1], segments[0][2], s0, s1)
+        for pts_e, anc_e, stride_e, first, rows in segments[1:]:          # TV-loss edge points: field MLP + scatter only
+            if rows > 0:
+                call("f2b_mlp_bwd2", d_scene16[first:first + rows], feat16[first:first + rows], f_hidden[0, first:first + rows],
+                     f_hidden[1, first:first + rows] if nh_f else None, fparams16, int(nh_f), rows,
+                     dfeat16[first:first + rows], d_fparams, stream())
+                scatter(pts_e, anc_e, stride_e, first, first + rows)
+        main.wait_stream(side)
+        d_sparams = d_sparams / s_scale
+        d_fparams = d_fparams / f_scale
         # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
         bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
         renderer.nonfinite_flag_ = bad

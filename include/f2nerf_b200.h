@@ -159,6 +159,11 @@ int f2b_field_fwd_slots(const void* table_f16, const int* prim_pool, const float
                         int vol_stride, const int* ray_counts, int n_rays, int slot_size, int logit_only,
                         float* out_f32, void* feat_save_f16, void* stream);
 
+/* f2b_mlp_bwd on a row range of a larger saved batch: the two activation layers are passed as separate pointers
+ * (hidden1 NULL when n_hidden_matmuls == 0).  dparams is accumulated into, like f2b_mlp_bwd. */
+int f2b_mlp_bwd2(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,
+                 const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16, float* dparams_f32, void* stream);
+
 /* Implementation selection for f2b_mlp_fwd / f2b_mlp_bwd: 1 = tcgen05/TMEM kernels (default when
  * built), 0 = CUDA-core twin (validation).  Env F2B_MLP_IMPL overrides the default. */
 int f2b_set_mlp_impl(int impl);
@@ -204,6 +209,18 @@ int f2b_shader_prep_bwd(const void* d_mlp_in_f16 /* [P,32] */, const int* pts_id
 int f2b_shader_prep_bwd_f16(const void* d_mlp_in_f16 /* [P,32] */, const float* d_logit /* [P] */,
                             const int* pts_idx_bounds, const int* emb_idx, int n_rays, float inv_loss_scale,
                             float field_loss_scale, void* d_field_out_f16 /* [P,16] */, float* d_app_emb, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step — replaces torch::optim::Adam::step for one parameter tensor
+ * (built at src/ExpRunner.cpp:54 from Hash3DAnchored::OptimParamGroups, src/Field/Hash3DAnchored.cpp:124-150;
+ * stepped at ExpRunner.cpp:136) and, when shadow_f16 != NULL, the fp32->fp16 table copy of the next forward
+ * (Hash3DAnchored.cu:186).  Same arithmetic, order and roundings as the ATen elementwise sequence, in one pass.
+ * Only elements [0, n_live) are read/written (n_live % 4 == 0): pass the live prefix of the hash table
+ * (17/32 of the pool), n for the other parameters.  step = 1 for the first update.
+ * ------------------------------------------------------------------------------------------ */
+int f2b_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_live,
+                  double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                  void* shadow_f16 /* [n] fp16 or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Composite — replaces the Renderer::Render tail (src/Renderer/Renderer.cpp:107-150,196-208),

@@ -490,3 +490,68 @@ def test_octree_votes_bit_exact(scene, oracle):
     np.testing.assert_array_equal(N(ps.tree_alpha_stats_), sa)
     np.testing.assert_array_equal(N(ps.tree_nodes_gpu_), nodes_ref)          # trans_idx = -1 pruning, byte for byte
     assert (nodes_ref != scene["nodes"]).any(), "test inputs must prune at least one node"
+
+
+# ---------------------------------------------------------------------- optimizer ----
+def aten_adam_step(p, g, m, v, step, lr, b1, b2, eps, wd):
+    """torch::optim::Adam::step of the C++ frontend (torch/csrc/api/src/optim/adam.cpp), op for op: the very ATen
+    kernels the reference runs (src/ExpRunner.cpp:136)."""
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    if wd != 0:
+        g = g.add(p, alpha=wd)
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-6])
+def test_fused_adam_bit_exact_vs_aten_sequence(wd):
+    from f2nerf_b200._lib import call, stream
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    n = 1 << 20
+    p0 = (torch.rand(n, device=DEV, generator=gen) * 2 - 1) * 1e-2
+    pa, pf = p0.clone(), p0.clone()
+    ma, va, mf, vf = (torch.zeros(n, device=DEV) for _ in range(4))
+    shadow = torch.zeros(n, dtype=torch.float16, device=DEV)
+    for step in range(1, 6):
+        g = torch.randn(n, device=DEV, generator=gen) * 10.0 ** float(torch.randint(-8, -2, (1,)).item())
+        g[torch.rand(n, device=DEV, generator=gen) < 0.7] = 0.0          # mostly-empty gradient, like the hash table's
+        lr = 1e-2 * (0.5 + 0.1 * step)
+        aten_adam_step(pa, g, ma, va, step, lr, 0.9, 0.99, 1e-15, wd)
+        call("f2b_adam_step", pf, g, mf, vf, n, n, lr, 0.9, 0.99, 1e-15, wd, step, shadow, stream())
+        for a, b, name in ((pa, pf, "param"), (ma, mf, "exp_avg"), (va, vf, "exp_avg_sq")):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (name, step, wd)
+        assert torch.equal(shadow, pf.to(torch.float16))
+
+
+def test_fused_adam_table_live_prefix_and_shadow(scene):
+    """FusedAdam on a real field: the table's dead 15/32 stays untouched, the cached fp16 shadow equals a fresh cast,
+    and three training steps give bit-identical parameters to the ATen sequence applied to the same gradients."""
+    from f2nerf_b200 import FusedAdam, TRAIN
+    from test_gpu_render import build
+    from conftest import make_rays
+    gdp, sampler, field, shader, renderer = build(scene)
+    gdp.mode_, gdp.learning_rate_ = TRAIN, 1e-2
+    opt = FusedAdam(renderer.OptimParamGroups(), table_field=field)
+    ref = {id(p): (p.detach().clone(), torch.zeros_like(p), torch.zeros_like(p)) for g in opt.param_groups for p in g["params"]}
+    dead0 = field.feat_pool_.detach().reshape(-1)[17 * field.local_size_:].clone()
+    o, d, dn, cam = make_rays(scene, 96, seed=4)
+    for step in range(1, 4):
+        opt.zero_grad()
+        torch.manual_seed(step)
+        r = renderer.Render(T(o), T(d), None, T(cam))
+        loss = (r.colors ** 2).mean() + 0.1 * ((r.edge_feats[:, 0] - r.edge_feats[:, 1]) ** 2).mean()
+        loss.backward()
+        for g in opt.param_groups:
+            for p in g["params"]:
+                pr, m, v = ref[id(p)]
+                pr.copy_(p.detach())                                     # same starting point (guards against drift bookkeeping)
+                aten_adam_step(pr, p.grad, m, v, step, g["lr"], *g["betas"], g["eps"], g.get("weight_decay", 0.0))
+        opt.step()
+        for g in opt.param_groups:
+            for p in g["params"]:
+                assert torch.equal(p.detach().view(torch.int32), ref[id(p)][0].view(torch.int32)), (step, tuple(p.shape))
+        assert torch.equal(field.table_f16(), field.feat_pool_.detach().to(torch.float16))
+    assert torch.equal(field.feat_pool_.detach().reshape(-1)[17 * field.local_size_:], dead0)
+    assert float((field.feat_pool_.grad.reshape(-1)[17 * field.local_size_:]).abs().max()) == 0.0
