@@ -171,6 +171,16 @@ int main(int argc, char** argv) {
     dump("grad_feat_pool_nz_idx", nz.to(torch::kInt32));
     dump("grad_feat_pool_nz_val", g.index({nz}));
     dump_scalar("backward_nan", gdp->backward_nan_ ? 1.f : 0.f);
+    // ---- the optimizer step the trainer takes next (ExpRunner.cpp:54,136): torch::optim::Adam over the field's groups
+    if (full_grads) {
+      dump("feat_pool_before_adam", field->feat_pool_.detach().reshape({-1}));
+      dump("field_mlp_before_adam", field->mlp_->params_.detach().reshape({-1}));
+      torch::optim::Adam opt(field->OptimParamGroups());
+      for (int it = 0; it < 2; it++) opt.step();                 // same gradient twice: exercises step 1 and step 2 bias corrections
+      dump("feat_pool_after_adam", field->feat_pool_.detach().reshape({-1}));
+      dump("field_mlp_after_adam", field->mlp_->params_.detach().reshape({-1}));
+      dump_scalar("adam_lr", gdp->learning_rate_);
+    }
   }
   {   // replay of the RNG draws Render made, in its order.  Every TCNNWP forward allocates its output with
       // torch::rand (TCNNWP.cpp:143), so the early-stop MLP call sits between the background and the edge draws.

@@ -228,3 +228,24 @@ def test_render_train_vs_reference(ref):
     # level-slab in gpurun_out/ref_grad_parity.json.  (Before the RNG-stream fix in f2nerf_b200/rng.py this cosine
     # was 0.78: the TV-loss edge points were different draws.)
     assert summary["feat_pool"]["cos"] >= 0.97, summary
+
+
+def test_fused_adam_vs_reference_optimizer(ref):
+    """SURVEY 8f N1: f2b_adam_step against the reference's own torch::optim::Adam (C++ frontend, ExpRunner.cpp:54,136)
+    stepping its own parameters with its own gradients twice — bit-identical parameters, table and MLP group."""
+    if "feat_pool_after_adam" not in ref:
+        pytest.skip("ref_driver without the optimizer dump")
+    from f2nerf_b200._lib import call, stream
+    lr = float(ref["adam_lr"][0])
+    pool = ref["feat_pool_before_adam"].shape[0]
+    local = ((pool // 2 // 16) >> 4) << 4
+    for name, wd, n_live in (("feat_pool", 0.0, 17 * local), ("field_mlp", 1e-6, None)):
+        p, g = T(ref[name + "_before_adam"]).clone(), T(ref["grad_" + name].reshape(-1))
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        n = p.numel()
+        for step in (1, 2):
+            call("f2b_adam_step", p, g, m, v, n, n if n_live is None else n_live, lr, 0.9, 0.99, 1e-15, wd, step, None, stream())
+        want = ref[name + "_after_adam"]
+        got = N(p)
+        assert (got != ref[name + "_before_adam"]).any()
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=name)
