@@ -393,7 +393,7 @@ def cpu_port(prob, args, budget_s=20.0):
         t = one(n)
     return {"value": n / t, "unit": "rays/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{n} of the {args.rays} rays of the same batch (all stages incl. backward), {t:.1f} s wall; "
-                      "sampler / hash encode / MLP forward / composite use OpenMP, the backward accumulations are single-threaded"}
+                      "all stages OpenMP-parallel (oracle/f2_oracle.c)"}
 
 
 def run_reference(args):
@@ -402,6 +402,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "F2B_REF_THREADS" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host thread it can
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("F2B_REF_THREADS", str(os.cpu_count()))
     import torch  # noqa: F401
     # the CPU arm needs the same parameters; build them on the CPU without touching the GPU library
     import oracle_lib as O
@@ -456,7 +459,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--log2-table", dest="log2_table", type=int, default=LOG2_TABLE)
-    ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=128)
+    ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()

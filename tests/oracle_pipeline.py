@@ -16,7 +16,8 @@ def f16(x):
 
 
 def render_train(sc, rays_o, rays_dn, noise, bg, field, shader_params, app_emb=None, emb_idx=None, edge=None,
-                 gt_colors=None, scales=None, gs_progress=1.0, backward=True, loss_w=(1.0, 0.01, 0.01, 0.1)):
+                 gt_colors=None, scales=None, gs_progress=1.0, backward=True, loss_w=(1.0, 0.01, 0.01, 0.1),
+                 diagnostics=False):
     """sc: dict(nodes, trans, edges, near, sample_l, scale_by_dis, max_hits)
     field: dict(table16 [pool,2] f16, prim, bias, V, local_size, mlp_params f32)
     edge: (edge_idx [n], edge_coord [n,2]) or None.  Returns dict of forward outputs (+ grads)."""
@@ -100,6 +101,10 @@ def render_train(sc, rays_o, rays_dn, noise, bg, field, shader_params, app_emb=N
     out["grad_feat_pool"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
                                        np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32), 1.0 / LOSS_SCALE,
                                        field["table16"].shape[0])
+    out["d_scene"] = d_scene
+    if not diagnostics:
+        return out
+    # ---- diagnostics only (tests/test_ref_parity.py): emulations of the reference's fp16 arithmetic ------------------
     # the same scatter with the reference's per-product fp16 rounding (Hash3DAnchored.cu:145-151) emulated
     out["grad_feat_pool_half_products"] = O.hash_bwd(field["prim"], field["bias"], field["V"], field["local_size"], scales,
                                                      np.ascontiguousarray(q_pts), q_vol, 1, d_feat16.astype(np.float32),

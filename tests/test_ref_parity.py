@@ -196,7 +196,7 @@ def test_render_train_vs_reference(ref):
                local_size=field.local_size_, mlp_params=ref["field_mlp_params"])
     orc = OP.render_train(sc, ref["rays_o"], ref["rays_d_normed"], ref["train_noise"], ref["train_bg"], fld, ref["shader_mlp_params"],
                           ref["app_emb"], ref["emb_idx"], (ref["train_edge_idx"], ref["train_edge_coord"]), ref["gt_colors"],
-                          scales=ops.hash_level_scales().numpy(), gs_progress=0.25)
+                          scales=ops.hash_level_scales().numpy(), gs_progress=0.25, diagnostics=True)
     def cosd(x, y):
         x, y = np.asarray(x, np.float64).reshape(-1), np.asarray(y, np.float64).reshape(-1)
         return float((x * y).sum() / (np.linalg.norm(x) * np.linalg.norm(y) + 1e-30))
