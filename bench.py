@@ -300,12 +300,38 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_port(prob, args, budget_s=20.0)
         if world == 1:
             line["optimizer_step"] = optimizer_timing(prob)
+            line["forward_only"] = forward_only_timing(prob, d_o, d_d, args)
         ref_gpu = reference_gpu_timing(args)
         if ref_gpu is not None:
             line["reference_gpu"] = ref_gpu
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def forward_only_timing(prob, d_o, d_d, args, iters=20):
+    """Forward-only rays/s (SURVEY 8d; the path ExpRunner::RenderWholeImage drives, ExpRunner.cpp:257-293): VALIDATE mode
+    (noise == 1, bg 0.5, no octree votes / edge samples), no autograd, same ray batch as the headline."""
+    import torch
+    from f2nerf_b200 import TRAIN, VALIDATE
+    gdp, r = prob["gdp"], prob["renderer"]
+    gdp.mode_ = VALIDATE
+    try:
+        with torch.no_grad():
+            for _ in range(3):
+                r.Render(d_o, d_d, None, None)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                r.Render(d_o, d_d, None, None)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        gdp.mode_ = TRAIN
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": args.rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
+            "note": "the reference's number is reference_gpu.ms_validate_median on the same ray count"}
 
 
 def optimizer_timing(prob, iters=20):

@@ -130,6 +130,28 @@ def test_render_mixed_empty_rays_and_ray_chunks(scene):
     assert np.isfinite(outs[0][0]).all()
 
 
+def test_render_whole_image_matches_chunked_render(scene):
+    """N4: RenderWholeImage == the reference's loop (ExpRunner.cpp:257-293) over our Render: same chunking (forced
+    small here), same normalisations, CPU outputs; ragged last chunk; rays that miss everything."""
+    from f2nerf_b200 import VALIDATE, RenderWholeImage
+    gdp, sampler, field, shader, renderer = build(scene, use_app_emb=False)
+    o, d, dn, cam = make_rays(scene, 700, seed=21)
+    o[5] = 600.; d[5] = 1.
+    pc, fo, pd = RenderWholeImage(renderer, torch.from_numpy(o), torch.from_numpy(d), None, ray_batch_size=256)
+    assert not pc.is_cuda and pc.shape == (700, 3) and fo.shape == (700, 1) and pd.shape == (700, 1)
+    gdp.mode_ = VALIDATE
+    cols, disp, first = [], [], []
+    with torch.no_grad():
+        for i in range(0, 700, 256):
+            r = renderer.Render(T(o[i:i + 256]), T(d[i:i + 256]), None, None)
+            cols.append(r.colors); disp.append(r.disparity.reshape(-1, 1)); first.append(r.first_oct_dis.reshape(-1, 1))
+    cols, disp, first = torch.cat(cols), torch.cat(disp), torch.cat(first)
+    np.testing.assert_array_equal(N(pc), N(cols))
+    np.testing.assert_array_equal(N(pd), N(disp / disp.max()))
+    np.testing.assert_array_equal(N(fo), N(first.min() / first))
+    assert (N(pc)[5] == 0.5).all()                                  # a ray that hits nothing shows the VALIDATE background
+
+
 def test_operator_level_autograd(scene, oracle):
     """Hash3DAnchored.AnchoredQuery / SHShader.Query as stand-alone differentiable operators."""
     gdp, sampler, field, shader, renderer = build(scene)
