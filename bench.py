@@ -301,6 +301,7 @@ def run_ours(args):
         if world == 1:
             line["optimizer_step"] = optimizer_timing(prob)
             line["forward_only"] = forward_only_timing(prob, d_o, d_d, args)
+            line["ray_generation"] = ray_generation_timing(prob, args)
         ref_gpu = reference_gpu_timing(args)
         if ref_gpu is not None:
             line["reference_gpu"] = ref_gpu
@@ -332,6 +333,54 @@ def forward_only_timing(prob, d_o, d_d, args, iters=20):
     ms = e0.elapsed_time(e1) / iters
     return {"value": args.rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
             "note": "the reference's number is reference_gpu.ms_validate_median on the same ray count"}
+
+
+def ray_generation_timing(prob, args, iters=20):
+    """SURVEY 8f N3 (reported separately): one training batch of rays + ground-truth colours.  `ours` =
+    RayGenerator.RandRaysData (CPU index draws, ONE 48 KB H2D copy, two kernels on HBM-resident images);
+    `reference_style` = the same draws followed by what Dataset::RandRaysData does (Dataset.cpp:287-296): CPU gather from
+    a CPU image tensor, three H2D copies, ray kernel.  ngp_fox geometry: 50 images of 960 x 540."""
+    import torch
+    from f2nerf_b200 import RayGenerator
+    sc = prob["scene"]
+    n_img, H, W = 50, 960, 540
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand((n_img, H, W, 3), generator=g)
+    c2w = np.asarray(sc.c2w, np.float32)
+    poses = np.tile(c2w[:1, :3, :4], (n_img, 1, 1)).astype(np.float32)
+    poses[:len(c2w)] = c2w[:n_img, :3, :4]
+    intri = np.tile(np.array([[687.6, 0, 270.], [0, 687.2, 480.], [0, 0, 1]], np.float32), (n_img, 1, 1))
+    dist = np.tile(np.array([0.057, -0.0787, -0.0019, -0.0025], np.float32), (n_img, 1))
+    bounds = np.tile(np.array([0.1, 10.], np.float32), (n_img, 1))
+    gen = RayGenerator(poses, intri, dist, bounds, images=images)
+    dev = gen.poses_.device
+    flat = images.view(-1, 3)
+
+    def ours():
+        gen.RandRaysData(args.rays)
+
+    def ref_style():
+        cam = torch.randint(n_img, (args.rays,), dtype=torch.int64)
+        i = torch.randint(0, H, (args.rays,), dtype=torch.int64)
+        j = torch.randint(0, W, (args.rays,), dtype=torch.int64)
+        ij = torch.stack([i, j], -1).to(dev).contiguous()
+        gt = flat[cam * H * W + i * W + j].to(dev).contiguous()
+        cam_d = cam.to(dev)
+        gen.Img2WorldRayFlex(cam_d.to(torch.int32), ij.to(torch.int32))
+        return gt, gen.bounds_[cam_d].contiguous()
+
+    out = {}
+    for name, fn in (("ours_ms", ours), ("reference_style_ms", ref_style)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        out[name] = (time.perf_counter() - t0) / iters * 1e3
+    out["note"] = "host wall time per 4096-ray batch incl. the CPU index draws; images 50x960x540x3 fp32"
+    return out
 
 
 def optimizer_timing(prob, iters=20):

@@ -211,6 +211,20 @@ int f2b_shader_prep_bwd_f16(const void* d_mlp_in_f16 /* [P,32] */, const float* 
                             float field_loss_scale, void* d_field_out_f16 /* [P,16] */, float* d_app_emb, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Ray generation — replaces Dataset::Img2WorldRayFlex / Img2WorldRayKernel incl. the Newton
+ * undistortion (src/Dataset/Dataset.cu:30-74,100-152) and the CPU ground-truth gather + H2D copy of
+ * Dataset::RandRaysData (src/Dataset/Dataset.cpp:290).  poses [n_cam,3,4], intri [n_cam,3,3], dist_params [n_cam,4]
+ * (k1,k2,p1,p2) fp32 row-major as Dataset holds them; cam_indices [n] i32; ij [n,2] i32 = (row, col), the +0.5 pixel
+ * centre is applied inside.  Bit-identical rays (operation order from the reference's PTX).
+ * ------------------------------------------------------------------------------------------ */
+int f2b_img2world_rays(const float* poses, const float* intri, const float* dist_params, const int* cam_indices,
+                       const int* ij, int n_rays, float* rays_o /* [n,3] */, float* rays_d /* [n,3], not normalised */,
+                       void* stream);
+/* out[r] = images[cam_indices[r], ij[r,0], ij[r,1], 0:3]; images fp32 [n_img, height, width, 3] resident on the device. */
+int f2b_gather_pixels(const float* images, const int* cam_indices, const int* ij, int height, int width, int n,
+                      float* out /* [n,3] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer step — replaces torch::optim::Adam::step for one parameter tensor
  * (built at src/ExpRunner.cpp:54 from Hash3DAnchored::OptimParamGroups, src/Field/Hash3DAnchored.cpp:124-150;
  * stepped at ExpRunner.cpp:136) and, when shadow_f16 != NULL, the fp32->fp16 table copy of the next forward

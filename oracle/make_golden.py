@@ -37,7 +37,8 @@ def main():
             "train_bounds", "train_colors", "train_disparity", "train_depth", "train_weights", "train_idx_start_end",
             "train_first_oct_dis", "train_tree_nodes_after", "train_weight_stats_after", "train_alpha_stats_after",
             "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb",
-            "edge_idx", "edge_coord", "edge_pts", "edge_anchors", "train_edge_feats"]
+            "edge_idx", "edge_coord", "edge_pts", "edge_anchors", "train_edge_feats",
+            "ds_poses", "ds_intri", "ds_dist_params", "ray_ij"]
     data = {k: np.load(os.path.join(out, k + ".npy")) for k in keep}
     for k in ("edge_idx", "edge_coord", "edge_pts", "edge_anchors"):         # 2048 of the 8192 draws are plenty
         data[k] = np.ascontiguousarray(data[k][:2048])

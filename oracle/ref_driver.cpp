@@ -103,6 +103,20 @@ int main(int argc, char** argv) {
   Tensor rays_o = rays.origins.contiguous(), rays_d = rays.dirs.contiguous(), bounds = rays.bounds.contiguous();
   dump("rays_o", rays_o); dump("rays_d", rays_d); dump("gt_colors", gt_colors); dump("emb_idx", emb_idx);
   dump("rays_d_normed", (rays_d / torch::linalg_norm(rays_d, 2, -1, true)).contiguous());
+  {   // ray generation: the camera tables and a replay of RandRaysData's CPU draws (Dataset.cpp:287-289)
+    dump("ds_poses", dataset->poses_.reshape({-1, 12})); dump("ds_intri", dataset->intri_.reshape({-1, 9}));
+    dump("ds_dist_params", dataset->dist_params_); dump("ds_bounds", dataset->bounds_); dump("ray_bounds", bounds);
+    Tensor hw = torch::zeros({2}, CUDAFloat); hw[0] = float(dataset->height_); hw[1] = float(dataset->width_);
+    dump("ds_hw", hw);
+    Tensor tset = torch::from_blob(dataset->train_set_.data(), {int(dataset->train_set_.size())}, CPUInt).clone().to(torch::kCUDA);
+    dump("ds_train_set", tset);
+    torch::manual_seed(2023);
+    Tensor cam = torch::randint(int(dataset->train_set_.size()), {n_rays}, CPULong);
+    Tensor ri = torch::randint(0, dataset->height_, n_rays, CPULong);
+    Tensor rj = torch::randint(0, dataset->width_, n_rays, CPULong);
+    dump("ray_ij", torch::stack({ri, rj}, -1).to(torch::kInt32).to(torch::kCUDA).contiguous());
+    dump("ray_cam_draw", cam.to(torch::kInt32).to(torch::kCUDA).contiguous());
+  }
 
   // ---- edge samples: the operator alone, with its RNG draws replayed next to it --------------------
   {

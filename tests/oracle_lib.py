@@ -211,5 +211,13 @@ def weight_var(w, bounds, dl_dvars=None):
     return out, dw
 
 
+def img2world_rays(poses, intri, dist_params, cam_indices, ij):
+    n = cam_indices.shape[0]
+    rays_o, rays_d = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    lib().orc_img2world_rays(_p(c(poses, np.float32)), _p(c(intri, np.float32)), _p(c(dist_params, np.float32)),
+                             _p(c(cam_indices, np.int32)), _p(c(ij, np.int32)), I(n), _p(rays_o), _p(rays_d))
+    return rays_o, rays_d
+
+
 def num_threads():
     return int(lib().orc_num_threads())

@@ -121,3 +121,13 @@ def test_early_stop_and_composite_vs_reference(g, oracle):
     for mine, name in ((w, "val_weights"), (colors, "val_colors"), (disp, "val_disparity"), (depth, "val_depth")):
         ref = g[name].reshape(mine.shape)
         np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-4 * max(np.abs(ref).max(), 1e-6), err_msg=name)
+
+
+def test_ray_generation_bit_exact_vs_reference(g, oracle):
+    """Img2WorldRayKernel + Newton undistortion (Dataset.cu:30-125): the oracle on the reference's own camera tables and
+    replayed pixel draws gives its rays bit for bit."""
+    if "ds_poses" not in g:
+        pytest.skip("fixture predates the ray-generation dump")
+    ro, rd = oracle.img2world_rays(g["ds_poses"], g["ds_intri"], g["ds_dist_params"], g["emb_idx"].astype(np.int32), g["ray_ij"])
+    np.testing.assert_array_equal(bits(ro), bits(g["rays_o"]))
+    np.testing.assert_array_equal(bits(rd), bits(g["rays_d"]))

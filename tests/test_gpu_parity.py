@@ -555,3 +555,38 @@ def test_fused_adam_table_live_prefix_and_shadow(scene):
         assert torch.equal(field.table_f16(), field.feat_pool_.detach().to(torch.float16))
     assert torch.equal(field.feat_pool_.detach().reshape(-1)[17 * field.local_size_:], dead0)
     assert float((field.feat_pool_.grad.reshape(-1)[17 * field.local_size_:]).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------- ray generation ----
+def test_img2world_rays_and_gather_vs_oracle(oracle):
+    """f2b_img2world_rays == the oracle (bit for bit) on cameras WITH lens distortion (the Newton iteration runs),
+    f2b_gather_pixels == index arithmetic; RayGenerator draws on the CPU generator like Dataset::RandRaysData."""
+    from f2nerf_b200 import RayGenerator
+    rng = np.random.default_rng(8)
+    n_cam, H, W, n = 7, 60, 90, 5000
+    poses = rng.standard_normal((n_cam, 3, 4)).astype(np.float32)
+    intri = np.zeros((n_cam, 3, 3), np.float32)
+    intri[:, 0, 0] = 80 + 10 * rng.random(n_cam); intri[:, 1, 1] = 80 + 10 * rng.random(n_cam)
+    intri[:, 0, 2] = W / 2 + rng.random(n_cam); intri[:, 1, 2] = H / 2 + rng.random(n_cam); intri[:, 2, 2] = 1
+    dist = (rng.standard_normal((n_cam, 4)) * np.array([0.1, 0.02, 1e-3, 1e-3])).astype(np.float32)
+    dist[0] = 0                                                       # one undistorted camera
+    bounds = rng.random((n_cam, 2)).astype(np.float32)
+    images = rng.random((n_cam, H, W, 3)).astype(np.float32)
+    gen = RayGenerator(poses, intri, dist, bounds, images=images, train_set=[0, 2, 3, 5, 6], test_set=[1, 4])
+    cam = rng.integers(0, n_cam, n).astype(np.int32)
+    ij = np.stack([rng.integers(0, H, n), rng.integers(0, W, n)], -1).astype(np.int32)
+    ro, rd = gen.Img2WorldRayFlex(T(cam), T(ij))
+    wo, wd = oracle.img2world_rays(poses, intri, dist, cam, ij)
+    np.testing.assert_array_equal(N(ro).view(np.uint32), wo.view(np.uint32))
+    np.testing.assert_array_equal(N(rd).view(np.uint32), wd.view(np.uint32))
+    torch.manual_seed(11)
+    (ro, rd, b), gt, cams = gen.RandRaysData(4096)
+    torch.manual_seed(11)
+    cur = torch.tensor([0, 2, 3, 5, 6], dtype=torch.int32)
+    c = cur[torch.randint(5, (4096,), dtype=torch.int64)].numpy()
+    i = torch.randint(0, H, (4096,), dtype=torch.int64).numpy(); j = torch.randint(0, W, (4096,), dtype=torch.int64).numpy()
+    np.testing.assert_array_equal(N(cams), c)
+    np.testing.assert_array_equal(N(gt), images[c, i, j])
+    np.testing.assert_array_equal(N(b), bounds[c])
+    wo, wd = oracle.img2world_rays(poses, intri, dist, c.astype(np.int32), np.stack([i, j], -1).astype(np.int32))
+    np.testing.assert_array_equal(N(rd).view(np.uint32), wd.view(np.uint32))

@@ -249,3 +249,33 @@ def test_fused_adam_vs_reference_optimizer(ref):
         got = N(p)
         assert (got != ref[name + "_before_adam"]).any()
         np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=name)
+
+
+def test_ray_generation_vs_reference(ref):
+    """SURVEY 8f N3: RayGenerator.RandRaysData reproduces Dataset::RandRaysData — same CPU draws under the same seed,
+    bit-identical rays (Newton undistortion included), bounds and camera indices."""
+    if "ds_poses" not in ref:
+        pytest.skip("ref_driver without the dataset dump")
+    from f2nerf_b200 import RayGenerator
+    h, w = int(ref["ds_hw"][0]), int(ref["ds_hw"][1])
+    gen = RayGenerator(ref["ds_poses"].reshape(-1, 3, 4), ref["ds_intri"].reshape(-1, 3, 3), ref["ds_dist_params"], ref["ds_bounds"],
+                       images=None, height=h, width=w, train_set=ref["ds_train_set"].tolist())
+    torch.manual_seed(2023)
+    (rays_o, rays_d, bounds), gt, cam = gen.RandRaysData(N_RAYS)
+    assert gt is None
+    bad = N(rays_d).view(np.uint32) != ref["rays_d"].view(np.uint32)
+    json.dump(dict(dist_params_abs_max=float(np.abs(ref["ds_dist_params"]).max()), n_rays=int(N_RAYS),
+                   frac_bad_per_component=bad.mean(0).tolist(), bad_rows=np.nonzero(bad.any(1))[0][:8].tolist(),
+                   sample=[dict(row=int(r), ours=N(rays_d)[r].tolist(), ref=ref["rays_d"][r].tolist(), cam=int(ref["emb_idx"][r]),
+                                ij=ref["ray_ij"][r].tolist()) for r in np.nonzero(bad.any(1))[0][:3]],
+                   dist_params=ref["ds_dist_params"][:3].tolist(), intri0=ref["ds_intri"][0].tolist(), pose0=ref["ds_poses"][0].tolist()),
+              open(os.path.join(ROOT, "gpurun_out", "ref_rays.json"), "w"))
+    np.testing.assert_array_equal(N(cam), ref["emb_idx"])
+    np.testing.assert_array_equal(N(rays_o).view(np.uint32), ref["rays_o"].view(np.uint32))
+    np.testing.assert_array_equal(N(rays_d).view(np.uint32), ref["rays_d"].view(np.uint32))
+    np.testing.assert_array_equal(N(bounds), ref["ray_bounds"])
+    # the kernel alone on the replayed draws
+    o2, d2 = gen.Img2WorldRayFlex(T(ref["emb_idx"].astype(np.int32)), T(ref["ray_ij"]))
+    np.testing.assert_array_equal(N(d2).view(np.uint32), ref["rays_d"].view(np.uint32))
+    json.dump(dict(dist_params_abs_max=float(np.abs(ref["ds_dist_params"]).max()), n_rays=int(N_RAYS)),
+              open(os.path.join(ROOT, "gpurun_out", "ref_rays.json"), "w"))
