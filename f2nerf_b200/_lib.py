@@ -51,6 +51,8 @@ SIGNATURES = {
     "f2b_mlp_fwd": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_f32": [_P, _P, c_int, c_int, _P, _P, _P, _P],
     "f2b_mlp_bwd": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "f2b_field_shade_fwd": [_P, _P, _P, _P, _P, c_int, _P, _P, _P, _P],
+    "f2b_shader_mlp_rgb_fwd": [_P, _P, c_int, _P, _P, _P, _P],
     "f2b_mlp_bwd2": [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_fwd_v0": [_P, _P, c_int, c_int, _P, _P, _P],
     "f2b_mlp_bwd_v0": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],

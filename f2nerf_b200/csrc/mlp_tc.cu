@@ -20,6 +20,7 @@
 //     CTAs share an SM (shared-memory bound) and overlap each other's MMA round trips.
 #include "common.cuh"
 #include "tc.cuh"
+#include "shader.cuh"
 
 namespace f2b {
 using namespace tc;
@@ -108,10 +109,25 @@ __device__ __forceinline__ void relu_epilogue(uint32_t tmem_row, unsigned char* 
   }
 }
 
-template <int NH>
+// Work that follows (or precedes) the MLP in Renderer::Render, done in its output epilogue while the row is in registers:
+//   EPI_SHADE (field MLP, NH = 0): the shading-feature assembly of Renderer.cpp:179-187 + SHShader.cpp:23-26 — the thread
+//     turns its 16 outputs into the shader MLP's fp16 input row ([1, feat 1..15] + appearance embedding | SH4(dir)) and
+//     the density logit; the fp32 [P,16] scene_feat tensor and the separate assembly kernel disappear;
+//   EPI_RGB (shader MLP, NH = 1): the scaled sigmoid of SHShader.cpp:27-28 -> rgb [P,3] next to the raw fp16 output.
+enum { EPI_NONE = 0, EPI_SHADE = 1, EPI_RGB = 2 };
+struct EpiArgs {
+  const float* dirs;          // [P,3]                     (SHADE)
+  const float* app_emb;       // [n_emb,16] or NULL         (SHADE)
+  const int* pt_emb_idx;      // [P] or NULL                (SHADE)
+  float* logit;               // [P]                        (SHADE)
+  __half* mlp_in;             // [P,32]                     (SHADE)
+  float* rgb;                 // [P,3]                      (RGB)
+};
+
+template <int NH, int EPI>
 __global__ void __launch_bounds__(kTcTile)
 mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ params, int n_pts,
-                  __half* __restrict__ out, float* __restrict__ out_f32, __half* __restrict__ hidden_save) {
+                  __half* __restrict__ out, float* __restrict__ out_f32, __half* __restrict__ hidden_save, EpiArgs epi) {
   using S = TcSmem<NH>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -218,6 +234,48 @@ mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ para
           dst[0] = make_float4(a.x, a.y, b.x, b.y); dst[1] = make_float4(c.x, c.y, d.x, d.y);
           dst[2] = make_float4(e.x, e.y, f.x, f.y); dst[3] = make_float4(u.x, u.y, w.x, w.y);
         }
+        if (EPI == EPI_RGB) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v0.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v0.y));
+          float* dst = epi.rgb + size_t(p) * 3;
+          dst[0] = shade_act(a.x); dst[1] = shade_act(a.y); dst[2] = shade_act(b.x);
+        }
+      }
+      if (EPI == EPI_SHADE) {
+        // my row of the shader MLP's input, staged in the (now dead) input tile of this iteration and copied out as whole
+        // lines by all threads; the density logit goes out directly (4 B per thread, contiguous per warp)
+        unsigned char* stage = sm + S::A0 + buf * 8192;
+        uint4 row[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (valid) {
+          uint4 v0, v1;
+          v0.x = pack_half2(__uint_as_float(r[0]), __uint_as_float(r[1]));   v0.y = pack_half2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          v0.z = pack_half2(__uint_as_float(r[4]), __uint_as_float(r[5]));   v0.w = pack_half2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+          v1.x = pack_half2(__uint_as_float(r[8]), __uint_as_float(r[9]));   v1.y = pack_half2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+          v1.z = pack_half2(__uint_as_float(r[12]), __uint_as_float(r[13])); v1.w = pack_half2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+          float feat[16];
+          const __half2* h = reinterpret_cast<const __half2*>(&v0);
+          const __half2* g = reinterpret_cast<const __half2*>(&v1);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float2 a = __half22float2(h[k]), b = __half22float2(g[k]);
+            feat[2 * k] = a.x; feat[2 * k + 1] = a.y; feat[8 + 2 * k] = b.x; feat[8 + 2 * k + 1] = b.y;
+          }
+          epi.logit[p] = feat[0];
+          const float* emb_row = epi.app_emb ? epi.app_emb + size_t(__ldg(epi.pt_emb_idx + p)) * 16 : nullptr;
+          shade_row(feat, emb_row, __ldg(epi.dirs + size_t(p) * 3), __ldg(epi.dirs + size_t(p) * 3 + 1),
+                    __ldg(epi.dirs + size_t(p) * 3 + 2), row);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(stage + sw64_off(tid, c)) = row[c];
+        __syncthreads();
+        const int rows = min(kTcTile, n_pts - tile * kTcTile);
+        uint4* dst = reinterpret_cast<uint4*>(epi.mlp_in + size_t(tile) * kTcTile * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = tid + kTcTile * j, rr = c >> 2;
+          if (rr < rows) dst[c] = *reinterpret_cast<const uint4*>(stage + sw64_off(rr, c & 3));
+        }
+        __syncthreads();                                         // the stage is the next-but-one tile's prefetch target
       }
     }
     // the next iteration's barrier orders these TMEM reads before the next tile's first MMA
@@ -232,17 +290,17 @@ mlp_fwd_tc_kernel(const __half* __restrict__ in, const __half* __restrict__ para
 
 using namespace f2b;
 
-template <int NH>
+template <int NH, int EPI>
 static void launch_fwd(const void* in_f16, const void* params_f16, int n_pts, void* out_f16, float* out_f32,
-                       void* hidden_save_f16, void* stream) {
+                       void* hidden_save_f16, const EpiArgs& epi, void* stream) {
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   const int per_sm = NH ? 3 : 5;                                  // shared-memory bound (63 KB / 39 KB per CTA)
   const int n_tiles = div_up(n_pts, kTcTile);
   const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
-  cudaFuncSetAttribute(mlp_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<NH>::BYTES);
-  mlp_fwd_tc_kernel<NH><<<grid, kTcTile, TcSmem<NH>::BYTES, as_stream(stream)>>>(
-      (const __half*)in_f16, (const __half*)params_f16, n_pts, (__half*)out_f16, out_f32, (__half*)hidden_save_f16);
+  cudaFuncSetAttribute(mlp_fwd_tc_kernel<NH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<NH>::BYTES);
+  mlp_fwd_tc_kernel<NH, EPI><<<grid, kTcTile, TcSmem<NH>::BYTES, as_stream(stream)>>>(
+      (const __half*)in_f16, (const __half*)params_f16, n_pts, (__half*)out_f16, out_f32, (__half*)hidden_save_f16, epi);
 }
 
 extern "C" int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
@@ -250,19 +308,53 @@ extern "C" int f2b_mlp_fwd_tc(const void* in_f16, const void* params_f16, int n_
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(in_f16 && params_f16 && out_f16, "f2b_mlp_fwd: null pointer");
   F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_fwd: n_hidden_matmuls must be 0 or 1");
-  if (n_hidden_matmuls == 0) launch_fwd<0>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, stream);
-  else launch_fwd<1>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, stream);
+  const EpiArgs none = {};
+  if (n_hidden_matmuls == 0) launch_fwd<0, EPI_NONE>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, none, stream);
+  else launch_fwd<1, EPI_NONE>(in_f16, params_f16, n_pts, out_f16, nullptr, hidden_save_f16, none, stream);
   return check_launch("f2b_mlp_fwd(tcgen05)");
 }
 
 // Same network, output widened to fp32 in the epilogue (what TCNNWP::Query hands back, TCNNWP.cpp:112):
 // out_f32 [P,16] and/or out_f16 [P,16] (either may be NULL, not both).
 extern "C" int f2b_mlp_fwd_tc_f32(const void* in_f16, const void* params_f16, int n_hidden_matmuls, int n_pts,
-                               float* out_f32, void* out_f16, void* hidden_save_f16, void* stream) {
+                                  float* out_f32, void* out_f16, void* hidden_save_f16, void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(in_f16 && params_f16 && (out_f32 || out_f16), "f2b_mlp_fwd_f32: null pointer");
   F2B_REQUIRE(n_hidden_matmuls == 0 || n_hidden_matmuls == 1, "f2b_mlp_fwd_f32: n_hidden_matmuls must be 0 or 1");
-  if (n_hidden_matmuls == 0) launch_fwd<0>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, stream);
-  else launch_fwd<1>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, stream);
+  const EpiArgs none = {};
+  if (n_hidden_matmuls == 0) launch_fwd<0, EPI_NONE>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, none, stream);
+  else launch_fwd<1, EPI_NONE>(in_f16, params_f16, n_pts, out_f16, out_f32, hidden_save_f16, none, stream);
   return check_launch("f2b_mlp_fwd_f32(tcgen05)");
+}
+
+// Field MLP (32 -> 64 -> 16) on encoded features + the shading-feature assembly in its epilogue:
+// logit[p] = out[p,0]; mlp_in[p] = fp16([1, out[p,1:16]] + app_emb[pt_emb_idx[p]] | SH4(dirs[p])).
+extern "C" int f2b_get_mlp_impl(void);
+#define F2B_REQUIRE_TC(name)                                                                                   \
+  if (f2b_get_mlp_impl() != 1) { set_error(name ": needs the tcgen05 MLP implementation (F2B_MLP_IMPL=1)"); return F2B_EUNSUPPORTED; }
+
+extern "C" int f2b_field_shade_fwd(const void* feat_f16, const void* field_params_f16, const float* dirs, const float* app_emb,
+                                   const int* pt_emb_idx, int n_pts, float* logit, void* mlp_in_f16, void* hidden_save_f16,
+                                   void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE_TC("f2b_field_shade_fwd")
+  F2B_REQUIRE(feat_f16 && field_params_f16 && dirs && logit && mlp_in_f16, "f2b_field_shade_fwd: null pointer");
+  F2B_REQUIRE(!app_emb || pt_emb_idx, "f2b_field_shade_fwd: app_emb without pt_emb_idx");
+  EpiArgs e = {};
+  e.dirs = dirs; e.app_emb = app_emb; e.pt_emb_idx = pt_emb_idx; e.logit = logit; e.mlp_in = (__half*)mlp_in_f16;
+  launch_fwd<0, EPI_SHADE>(feat_f16, field_params_f16, n_pts, nullptr, nullptr, hidden_save_f16, e, stream);
+  return check_launch("f2b_field_shade_fwd");
+}
+
+// Shader MLP (32 -> 64 -> 64 -> 16) + the colour activation in its epilogue: raw [P,16] fp16 (the backward needs it)
+// and rgb [P,3] = (1 + 2e-3) * sigmoid(raw[:, :3]) - 1e-3.
+extern "C" int f2b_shader_mlp_rgb_fwd(const void* mlp_in_f16, const void* shader_params_f16, int n_pts, void* raw_f16,
+                                      float* rgb, void* hidden_save_f16, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE_TC("f2b_shader_mlp_rgb_fwd")
+  F2B_REQUIRE(mlp_in_f16 && shader_params_f16 && raw_f16 && rgb, "f2b_shader_mlp_rgb_fwd: null pointer");
+  EpiArgs e = {};
+  e.rgb = rgb;
+  launch_fwd<1, EPI_RGB>(mlp_in_f16, shader_params_f16, n_pts, raw_f16, nullptr, hidden_save_f16, e, stream);
+  return check_launch("f2b_shader_mlp_rgb_fwd");
 }

@@ -7,29 +7,9 @@
 // tiny-cuda-nn's identity encoding cast (encodings/identity.h:45-85) and the sigmoid of
 // SHShader::Query (src/Shader/SHShader.cpp:27-28).
 #include "common.cuh"
+#include "shader.cuh"
 
 namespace f2b {
-
-// degree-4 real spherical harmonics in tiny-cuda-nn ordering (SHShader.cu:32-50)
-__device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
-  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-  o[0] = 0.28209479177387814f;
-  o[1] = -0.48860251190291987f * y;
-  o[2] = 0.48860251190291987f * z;
-  o[3] = -0.48860251190291987f * x;
-  o[4] = 1.0925484305920792f * xy;
-  o[5] = -1.0925484305920792f * yz;
-  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-  o[7] = -1.0925484305920792f * xz;
-  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-  o[10] = 2.8906114426405538f * xy * z;
-  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-  o[14] = 1.4453057213202769f * z * (x2 - y2);
-  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
 
 __global__ void sh_encode_kernel(const float* __restrict__ dirs, int n, int degree, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,42 +37,24 @@ shader_prep_kernel(const float* __restrict__ scene_feat, const float* __restrict
                    __half* __restrict__ mlp_in) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v[32];
+  float feat[16];
   const float4* f4 = reinterpret_cast<const float4*>(scene_feat + size_t(i) * 16);
 #pragma unroll
-  for (int q = 0; q < 4; q++) { const float4 a = __ldg(f4 + q); v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w; }
-  v[0] = 1.f;
-  if (app_emb) {
-    const float4* e4 = reinterpret_cast<const float4*>(app_emb + size_t(pt_emb_idx[i]) * 16);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const float4 a = __ldg(e4 + q);
-      v[4 * q] = fadd(v[4 * q], a.x); v[4 * q + 1] = fadd(v[4 * q + 1], a.y);
-      v[4 * q + 2] = fadd(v[4 * q + 2], a.z); v[4 * q + 3] = fadd(v[4 * q + 3], a.w);
-    }
-  }
-  sh4(__ldg(dirs + size_t(i) * 3), __ldg(dirs + size_t(i) * 3 + 1), __ldg(dirs + size_t(i) * 3 + 2), v + 16);
+  for (int q = 0; q < 4; q++) { const float4 a = __ldg(f4 + q); feat[4 * q] = a.x; feat[4 * q + 1] = a.y; feat[4 * q + 2] = a.z; feat[4 * q + 3] = a.w; }
+  uint4 row[4];
+  shade_row(feat, app_emb ? app_emb + size_t(pt_emb_idx[i]) * 16 : nullptr, __ldg(dirs + size_t(i) * 3),
+            __ldg(dirs + size_t(i) * 3 + 1), __ldg(dirs + size_t(i) * 3 + 2), row);
   uint4* dst = reinterpret_cast<uint4*>(mlp_in + size_t(i) * 32);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    __half2 h[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(v[8 * q + 2 * k], v[8 * q + 2 * k + 1]);
-    dst[q] = *reinterpret_cast<uint4*>(h);
-  }
+  for (int q = 0; q < 4; q++) dst[q] = row[q];
 }
 
 // rgb = (1 + 2e-3) / (1 + exp(-o)) - 1e-3 on the fp16 MLP output (SHShader.cpp:27-28)
 __global__ void shader_act_kernel(const __half* __restrict__ raw, int n, float* __restrict__ rgb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float eps = 1e-3f;
-  const float c = 1.f + 2.f * eps;
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const float o = __half2float(raw[size_t(i) * 16 + k]);
-    rgb[size_t(i) * 3 + k] = fsub(fdiv(c, fadd(1.f, expf(-o))), eps);
-  }
+  for (int k = 0; k < 3; k++) rgb[size_t(i) * 3 + k] = shade_act(__half2float(raw[size_t(i) * 16 + k]));
 }
 
 // dL/d raw_out (fp16, times loss_scale) from dL/d rgb; channels 3..15 get zero.

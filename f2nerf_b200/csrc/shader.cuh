@@ -1,0 +1,65 @@
+// shader.cuh — device functions shared by shader.cu (stand-alone operators) and mlp_tc.cu (the same work fused into
+// the tcgen05 MLP epilogues).  Explicit roundings: both users produce bit-identical rows.
+#pragma once
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace f2b {
+
+// degree-4 real spherical harmonics in tiny-cuda-nn ordering (SHShader.cu:32-50); every product / sum rounded
+// separately (no contraction), so the stand-alone operator and the fused epilogue agree bit for bit
+__device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
+  const float xy = fmul(x, y), xz = fmul(x, z), yz = fmul(y, z), x2 = fmul(x, x), y2 = fmul(y, y), z2 = fmul(z, z);
+  o[0] = 0.28209479177387814f;
+  o[1] = fmul(-0.48860251190291987f, y);
+  o[2] = fmul(0.48860251190291987f, z);
+  o[3] = fmul(-0.48860251190291987f, x);
+  o[4] = fmul(1.0925484305920792f, xy);
+  o[5] = fmul(-1.0925484305920792f, yz);
+  o[6] = fsub(fmul(0.94617469575755997f, z2), 0.31539156525251999f);
+  o[7] = fmul(-1.0925484305920792f, xz);
+  o[8] = fsub(fmul(0.54627421529603959f, x2), fmul(0.54627421529603959f, y2));
+  o[9] = fmul(fmul(0.59004358992664352f, y), fadd(fmul(-3.0f, x2), y2));
+  o[10] = fmul(fmul(2.8906114426405538f, xy), z);
+  o[11] = fmul(fmul(0.45704579946446572f, y), fsub(1.0f, fmul(5.0f, z2)));
+  o[12] = fmul(fmul(0.3731763325901154f, z), fsub(fmul(5.0f, z2), 3.0f));
+  o[13] = fmul(fmul(0.45704579946446572f, x), fsub(1.0f, fmul(5.0f, z2)));
+  o[14] = fmul(fmul(1.4453057213202769f, z), fsub(x2, y2));
+  o[15] = fmul(fmul(0.59004358992664352f, x), fadd(-x2, fmul(3.0f, y2)));
+}
+
+// Shader-MLP input row: fp16([1, feat[1..15]] + app_emb[cam] | SH4(dir)) (Renderer.cpp:179-187, SHShader.cpp:23-26,
+// identity-encoding cast).  feat[0..15] = the field output (fp16-rounded values), feat[0] is ignored.
+__device__ __forceinline__ void shade_row(const float feat[16], const float* __restrict__ emb_row /* nullable */,
+                                          float dx, float dy, float dz, uint4 row[4]) {
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] = feat[k];
+  v[0] = 1.f;
+  if (emb_row) {
+    const float4* e4 = reinterpret_cast<const float4*>(emb_row);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 a = __ldg(e4 + q);
+      v[4 * q] = fadd(v[4 * q], a.x); v[4 * q + 1] = fadd(v[4 * q + 1], a.y);
+      v[4 * q + 2] = fadd(v[4 * q + 2], a.z); v[4 * q + 3] = fadd(v[4 * q + 3], a.w);
+    }
+  }
+  sh4(dx, dy, dz, v + 16);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    __half2 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(v[8 * q + 2 * k], v[8 * q + 2 * k + 1]);
+    row[q] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// rgb = (1 + 2e-3) / (1 + exp(-o)) - 1e-3 on the fp16 MLP output (SHShader.cpp:27-28)
+__device__ __forceinline__ float shade_act(float o) {
+  const float eps = 1e-3f;
+  const float c = 1.f + 2.f * eps;
+  return fsub(fdiv(c, fadd(1.f, expf(-o))), eps);
+}
+
+}  // namespace f2b

@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import call, stream
 from .field import field_backward, field_forward, field_forward_from_features
 from .rng import burn_mlp_output, burn_rand
@@ -237,14 +237,37 @@ class _RenderFunction(torch.autograd.Function):
         field, shader = renderer.scene_field_, renderer.shader_
         fparams16 = ops.cast_f32_to_f16(field_params)
         sparams16 = ops.cast_f32_to_f16(shader_params)
-        scene_feat, f_hidden = field_forward_from_features(field, fparams16, feat16, save=grad_on)
+        dev = bg.device
+        n_q = feat16.shape[0]
         emb = app_emb if pt_emb_idx is not None else None
-        mlp_in = ops.shader_prep(scene_feat[:n_kept], es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
-            torch.empty((0, 32), dtype=torch.float16, device=bg.device)
-        raw, s_hidden = ops.mlp_fwd(mlp_in, sparams16, shader.mlp_.n_hidden_matmuls, save_hidden=grad_on)
-        rgb = ops.shader_act(raw)
-        colors, disparity, depth, weights = ops.composite_fwd(scene_feat, 16, rgb, es.dt, es.t, es.pts_idx_bounds, bg)
-        edge_feats = scene_feat[n_kept:].reshape(-1, 2, 16)
+        if _lib.lib.f2b_get_mlp_impl() == 1 and field.mlp_.n_hidden_matmuls == 0 and shader.mlp_.n_hidden_matmuls == 1:
+            # fused epilogues (tcgen05 kernels): field MLP -> [logit | shader-MLP input row], shader MLP -> [raw | rgb];
+            # the fp32 scene_feat of the ray samples is never materialised (edge points still need all 16 channels)
+            f_hidden = torch.empty((1, n_q, 64), dtype=torch.float16, device=dev) if grad_on else None
+            logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
+            mlp_in = torch.empty((n_kept, 32), dtype=torch.float16, device=dev)
+            call("f2b_field_shade_fwd", feat16, fparams16, es.dirs, emb, pt_emb_idx, n_kept, logit, mlp_in, f_hidden, stream())
+            if n_q > n_kept:
+                edge32 = torch.empty((n_q - n_kept, 16), dtype=torch.float32, device=dev)
+                call("f2b_mlp_fwd_f32", feat16[n_kept:], fparams16, 0, n_q - n_kept, edge32, None,
+                     f_hidden[0, n_kept:] if grad_on else None, stream())
+            else:
+                edge32 = torch.empty((0, 16), dtype=torch.float32, device=dev)
+            s_hidden = torch.empty((2, n_kept, 64), dtype=torch.float16, device=dev) if grad_on else None
+            raw = torch.empty((n_kept, 16), dtype=torch.float16, device=dev)
+            rgb = torch.empty((n_kept, 3), dtype=torch.float32, device=dev)
+            call("f2b_shader_mlp_rgb_fwd", mlp_in, sparams16, n_kept, raw, rgb, s_hidden, stream())
+            logit_stride = 1
+        else:
+            scene_feat, f_hidden = field_forward_from_features(field, fparams16, feat16, save=grad_on)
+            mlp_in = ops.shader_prep(scene_feat[:n_kept], es.dirs, emb, pt_emb_idx) if n_kept > 0 else \
+                torch.empty((0, 32), dtype=torch.float16, device=bg.device)
+            raw, s_hidden = ops.mlp_fwd(mlp_in, sparams16, shader.mlp_.n_hidden_matmuls, save_hidden=grad_on)
+            rgb = ops.shader_act(raw)
+            logit, logit_stride, edge32 = scene_feat, 16, scene_feat[n_kept:]
+        colors, disparity, depth, weights = ops.composite_fwd(logit, logit_stride, rgb, es.dt, es.t, es.pts_idx_bounds, bg)
+        scene_feat = (logit, logit_stride)
+        edge_feats = edge32.reshape(-1, 2, 16)
         ctx.renderer, ctx.es, ctx.n_kept = renderer, es, n_kept
         ctx.cuts = renderer._bwd_cuts_ if getattr(renderer, "_bwd_cuts_", None) else [(0, es.pts_idx_bounds.shape[0], 0, n_kept)]
         ctx.pack = (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
@@ -309,7 +332,7 @@ class _RenderFunction(torch.autograd.Function):
             if s1 <= s0:
                 continue
             nr, ns = r1 - r0, s1 - s0
-            call("f2b_composite_bwd", scene_feat, 16, rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr, d_colors[r0:r1],
+            call("f2b_composite_bwd", scene_feat[0], int(scene_feat[1]), rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr, d_colors[r0:r1],
                  None if d_disp is None else d_disp[r0:r1], None if d_depth is None else d_depth[r0:r1], d_weights,
                  float(ctx.gs_progress), d_logit, 1, d_rgb, stream())
             call("f2b_shader_act_bwd", raw[s0:s1], d_rgb[s0:s1], ns, float(s_scale), d_raw[s0:s1], stream())

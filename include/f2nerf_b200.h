@@ -159,6 +159,18 @@ int f2b_field_fwd_slots(const void* table_f16, const int* prim_pool, const float
                         int vol_stride, const int* ray_counts, int n_rays, int slot_size, int logit_only,
                         float* out_f32, void* feat_save_f16, void* stream);
 
+/* Field MLP on already-encoded features with the shading-feature assembly fused into its epilogue (the fp32 [P,16]
+ * scene_feat tensor, `ones_like`/`cat`/ScatterAdd of Renderer.cpp:179-187 and the SH encode + cast of SHShader.cpp:23-26
+ * never materialise): logit[p] = out[p,0]; mlp_in[p] = fp16([1, out[p,1:16]] + app_emb[pt_emb_idx[p]] | SH4(dirs[p])).
+ * tcgen05 implementation only (F2B_EUNSUPPORTED with the CUDA-core twin selected). */
+int f2b_field_shade_fwd(const void* feat_f16 /* [P,32] */, const void* field_params_f16, const float* dirs /* [P,3] */,
+                        const float* app_emb /* [n_emb,16] or NULL */, const int* pt_emb_idx /* [P] or NULL */, int n_pts,
+                        float* logit /* [P] */, void* mlp_in_f16 /* [P,32] */, void* hidden_save_f16 /* [P,64] or NULL */,
+                        void* stream);
+/* Shader MLP with the colour activation of SHShader.cpp:27-28 in its epilogue: raw [P,16] fp16 and
+ * rgb [P,3] = (1 + 2e-3) * sigmoid(raw[:, :3]) - 1e-3.  tcgen05 implementation only. */
+int f2b_shader_mlp_rgb_fwd(const void* mlp_in_f16, const void* shader_params_f16, int n_pts, void* raw_f16, float* rgb,
+                           void* hidden_save_f16 /* [2,P,64] or NULL */, void* stream);
 /* f2b_mlp_bwd on a row range of a larger saved batch: the two activation layers are passed as separate pointers
  * (hidden1 NULL when n_hidden_matmuls == 0).  dparams is accumulated into, like f2b_mlp_bwd. */
 int f2b_mlp_bwd2(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,

@@ -225,6 +225,38 @@ def test_mlp_tc_tiles_and_f32_output(oracle, nh):
         assert_close(N(dp), N(dp0), rtol=3e-3, atol_frac=2e-3, name=f"dparams n={n}")
 
 
+def test_fused_epilogues_match_operator_sequence(oracle):
+    """f2b_field_shade_fwd == mlp_fwd -> cast -> shader_prep and f2b_shader_mlp_rgb_fwd == mlp_fwd -> shader_act, bit for bit
+    (ragged sizes, with and without appearance embedding, across several tiles per CTA)."""
+    from f2nerf_b200 import ops
+    from f2nerf_b200._lib import call, stream
+    rng = np.random.default_rng(55)
+    fp = T((oracle.mlp_init(32, 0) * 3).astype(np.float16))
+    sp = T((oracle.mlp_init(32, 1) * 2).astype(np.float16))
+    emb = T((rng.standard_normal((11, 16)) * .1).astype(np.float32))
+    for n in (1, 129, 4000, 148 * 5 * 128 + 77):
+        feat = T((rng.standard_normal((n, 32)) * 0.5).astype(np.float16))
+        d = rng.standard_normal((n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        dirs, idx = T(d), T(rng.integers(0, 11, n).astype(np.int32))
+        out32, _, hid = ops.mlp_fwd_f32(feat, fp, 0, save_hidden=True)
+        for use_emb in (False, True):
+            want_in = ops.shader_prep(out32, dirs, emb if use_emb else None, idx if use_emb else None)
+            logit = torch.empty((n,), device=DEV); mlp_in = torch.empty((n, 32), dtype=torch.float16, device=DEV)
+            hid2 = torch.empty((1, n, 64), dtype=torch.float16, device=DEV)
+            call("f2b_field_shade_fwd", feat, fp, dirs, emb if use_emb else None, idx if use_emb else None, n, logit, mlp_in, hid2, stream())
+            np.testing.assert_array_equal(N(mlp_in).view(np.uint16), N(want_in).view(np.uint16))
+            np.testing.assert_array_equal(N(logit), N(out32)[:, 0])
+            np.testing.assert_array_equal(N(hid2).view(np.uint16), N(hid).view(np.uint16))
+        raw_w, shid_w = ops.mlp_fwd(want_in, sp, 1, save_hidden=True, impl="tc")
+        rgb_w = ops.shader_act(raw_w)
+        raw = torch.empty((n, 16), dtype=torch.float16, device=DEV); rgb = torch.empty((n, 3), device=DEV)
+        shid = torch.empty((2, n, 64), dtype=torch.float16, device=DEV)
+        call("f2b_shader_mlp_rgb_fwd", want_in, sp, n, raw, rgb, shid, stream())
+        np.testing.assert_array_equal(N(raw).view(np.uint16), N(raw_w).view(np.uint16))
+        np.testing.assert_array_equal(N(rgb), N(rgb_w))
+        np.testing.assert_array_equal(N(shid).view(np.uint16), N(shid_w).view(np.uint16))
+
+
 def test_fused_field_matches_unfused(scene, oracle, hash_params):
     """f2b_field_fwd (encode fused into the tcgen05 MLP) == f2b_hash_fwd -> f2b_mlp_fwd_tc, bit for bit."""
     from f2nerf_b200 import ops
