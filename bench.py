@@ -132,6 +132,7 @@ ALGO_BYTES = {  # algorithmic bytes per unit (sample) at the operator boundary â
 
 NCU_KERNEL = {"f2b_hash_bwd": "hash_bwd_kernel<1>", "f2b_sampler_march": "march16_kernel<2>",
               "f2b_field_fwd_slots": "field_fwd_kernel<1, 4>", "f2b_field_fwd": "field_fwd_kernel<1, 4>",
+              "f2b_mlp_bwd2": "mlp_bwd_tc_kernel<1>",
               "f2b_compact_slots": "compact_slots_kernel", "f2b_composite_fwd": "composite_fwd_kernel",
               "f2b_composite_bwd": "composite_bwd_kernel"}
 
@@ -196,6 +197,15 @@ def run_ours(args):
     barrier()
     clocks.rows.clear()                          # keep only samples taken under the timed regions
     def timed_loop():
+        import gc
+        gc.collect()
+        gc.disable()                              # like timeit: no cyclic-GC pause inside the timed region
+        try:
+            return _timed_loop()
+        finally:
+            gc.enable()
+
+    def _timed_loop():
         barrier()
         l0 = _lib.LAUNCHES
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,7 +229,7 @@ def run_ours(args):
     for _ in range(2):
         ms, walls, n_samples, n_kept, launches = timed_loop()
         med = sorted(walls)[len(walls) // 2]
-        outlier = max(walls) > 2.5 * med and max(walls) - med > 5.0
+        outlier = max(walls[1:] or walls) > 1.5 * med and max(walls[1:] or walls) - med > 2.5
         attempts.append({"ms_per_step": ms / args.steps, "host_wall_ms_per_step": walls, "rejected": bool(outlier)})
         if not outlier:
             break
