@@ -71,6 +71,8 @@ SIGNATURES = {
     "f2b_shader_act_bwd": [_P, _P, c_int, c_float, _P, _P],
     "f2b_shader_prep_bwd": [_P, _P, _P, c_int, c_float, _P, _P, _P],
     "f2b_shader_prep_bwd_f16": [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P],
+    "f2b_octree_proc": [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_octree_mark_invisible": [_P, c_int, _P, _P, _P, c_int, _P],
     "f2b_img2world_rays": [_P, _P, _P, _P, _P, c_int, _P, _P, _P],
     "f2b_gather_pixels": [_P, _P, _P, c_int, c_int, c_int, _P, _P],
     "f2b_adam_step": [_P, _P, _P, _P, c_i64, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,

@@ -29,7 +29,8 @@ struct __align__(32) TreeNode {      // 64 B
   float side_len;
   int   parent;
   int   childs[8];
-  int   is_leaf_node;                // bool @52 + 3 pad bytes
+  unsigned char is_leaf_node;        // bool @52 ...
+  unsigned char _pad0[3];            // ... + 3 padding bytes the reference never initialises
   int   trans_idx;                   // @56  (<0 => pruned / invalid: the "occupancy bit")
   int   _pad;
 };

@@ -225,6 +225,49 @@ class PersSampler:
         self.last_votes_ = (vote_w, vote_a, mark)
         self.apply_votes(vote_w, vote_a, mark)
 
+    # ---- octree maintenance on the device --------------------------------------------------------
+    def ProcOctree(self, compact=True, subdivide=False, brute_force=False):
+        """PersOctree::ProcOctree (PersSampler.cpp:120-330) without leaving the device: prune dead leaves, collapse
+        single-child chains, renumber, optionally split every leaf visited more than 4 times (or all, ``brute_force``).
+        Same numbering / links / statistics as the reference; one 4-byte readback (the new node count)."""
+        if not compact:
+            raise NotImplementedError("ProcOctree(compact=False): every call site of the reference compacts (PersSampler.cu:604-614)")
+        n, dev = self.n_nodes, self.tree_nodes_gpu_.device
+        work_nodes = torch.empty((n * 64,), dtype=torch.uint8, device=dev)
+        work_i32 = torch.empty((5 * n + 2,), dtype=torch.int32, device=dev)
+        cap = 9 * n if subdivide else n
+        nodes_out = torch.empty((cap * 64,), dtype=torch.uint8, device=dev)
+        w_out = torch.empty((cap,), dtype=torch.int32, device=dev)
+        a_out = torch.empty((cap,), dtype=torch.int32, device=dev)
+        n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
+        call("f2b_octree_proc", self.tree_nodes_gpu_, self.tree_weight_stats_, self.tree_alpha_stats_, self.tree_visit_cnt_, n,
+             int(bool(subdivide)), int(bool(brute_force)), work_nodes, work_i32, nodes_out, w_out, a_out, n_out, stream())
+        m = int(n_out.item())                                                    # the only host round trip
+        self.tree_nodes_gpu_ = nodes_out[:m * 64].clone()
+        self.tree_weight_stats_, self.tree_alpha_stats_ = w_out[:m].clone(), a_out[:m].clone()
+        self.tree_visit_cnt_ = torch.zeros((m,), dtype=torch.int32, device=dev)
+        return m
+
+    def MarkInvisibleNodes(self, intri, w2c, bounds):
+        """PersOctree::MarkInvisibleNodes (PersSampler.cu:645-680): intri [n,3,3], w2c [n,3,4], bounds [n,2] of the
+        training cameras (the reference keeps them in PersOctree; here the caller passes them)."""
+        f = lambda t: torch.as_tensor(t, dtype=torch.float32).to(self.tree_nodes_gpu_.device).contiguous()
+        intri, w2c, bounds = f(intri), f(w2c), f(bounds)
+        call("f2b_octree_mark_invisible", self.tree_nodes_gpu_, self.n_nodes, intri, w2c, bounds, intri.shape[0], stream())
+
+    def maintain(self, cameras=None, compact_freq=1000):
+        """The tail of PersSampler::UpdateOctNodes (PersSampler.cu:604-614): subdivision milestones, then the periodic
+        compaction.  ``cameras`` = (intri, w2c, bounds) for MarkInvisibleNodes (skipped when None)."""
+        it = self.global_data_pool_.iter_step_
+        while self.sub_div_milestones_ and self.sub_div_milestones_[-1] <= it:
+            self.ProcOctree(True, True, self.sub_div_milestones_[-1] <= 0)
+            if cameras is not None:
+                self.MarkInvisibleNodes(*cameras)
+            self.ProcOctree(True, False, False)
+            self.sub_div_milestones_.pop()
+        if compact_freq and it % compact_freq == 0:
+            self.ProcOctree(True, False, False)
+
     def apply_votes(self, vote_w, vote_a, mark):
         call("f2b_oct_update_stats", vote_w, vote_a, mark, self.tree_weight_stats_, self.tree_alpha_stats_,
              self.tree_nodes_gpu_, self.n_nodes, stream())

@@ -223,6 +223,22 @@ int f2b_shader_prep_bwd_f16(const void* d_mlp_in_f16 /* [P,32] */, const float* 
                             float field_loss_scale, void* d_field_out_f16 /* [P,16] */, float* d_app_emb, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Octree maintenance on the device — replaces PersOctree::ProcOctree(compact = true, subdivide,
+ * brute_force) (src/PtsSampler/PersSampler.cpp:120-330: prune dead leaves, collapse single-child chains, renumber,
+ * optionally split every leaf visited more than 4 times into 8; called from PersSampler::UpdateOctNodes,
+ * PersSampler.cu:604-614) and PersOctree::MarkInvisibleNodes (PersSampler.cu:616-680).  Same node numbering, links,
+ * centres and statistics as the reference's sequential host pass, without the three D2H + three H2D blob copies.
+ * work_nodes: [n_nodes] TreeNode scratch; work_i32: [5*n_nodes + 2] ints; outputs sized for 9*n_nodes nodes;
+ * n_nodes_out: device int (the only value the host has to read back); visit counts restart at zero (caller memsets).
+ * ------------------------------------------------------------------------------------------ */
+int f2b_octree_proc(const void* tree_nodes, const int* weight_stats, const int* alpha_stats, const int* visit_cnt,
+                    int n_nodes, int subdivide, int brute_force, void* work_nodes, int* work_i32, void* nodes_out,
+                    int* weight_stats_out, int* alpha_stats_out, int* n_nodes_out, void* stream);
+/* nodes no training camera can see get trans_idx = -1.  intri [n_cams,3,3], w2c [n_cams,3,4], bounds [n_cams,2]. */
+int f2b_octree_mark_invisible(void* tree_nodes, int n_nodes, const float* intri, const float* w2c, const float* bounds,
+                              int n_cams, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Ray generation — replaces Dataset::Img2WorldRayFlex / Img2WorldRayKernel incl. the Newton
  * undistortion (src/Dataset/Dataset.cu:30-74,100-152) and the CPU ground-truth gather + H2D copy of
  * Dataset::RandRaysData (src/Dataset/Dataset.cpp:290).  poses [n_cam,3,4], intri [n_cam,3,3], dist_params [n_cam,4]

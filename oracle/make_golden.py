@@ -24,7 +24,7 @@ N_RAYS = 12
 def main():
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     out = "/tmp/f2b_golden_dump"
-    r = subprocess.run([drv, os.path.join(ROOT, "oracle", "ref_config_ngp_fox.yaml"), out, str(N_RAYS), "0", "0"], cwd=ROOT,
+    r = subprocess.run([drv, os.path.join(ROOT, "oracle", "ref_config_ngp_fox.yaml"), out, str(N_RAYS), "0", "1"], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-4000:])
@@ -38,7 +38,9 @@ def main():
             "train_first_oct_dis", "train_tree_nodes_after", "train_weight_stats_after", "train_alpha_stats_after",
             "train_visit_cnt_after", "train_loss", "grad_field_mlp", "grad_shader_mlp", "grad_app_emb",
             "edge_idx", "edge_coord", "edge_pts", "edge_anchors", "train_edge_feats",
-            "ds_poses", "ds_intri", "ds_dist_params", "ray_ij"]
+            "ds_poses", "ds_intri", "ds_dist_params", "ray_ij",
+            "oct_nodes_in", "oct_w_in", "oct_a_in", "oct_visit_in", "oct_nodes_sub", "oct_w_sub", "oct_a_sub",
+            "oct_nodes_invis", "oct_nodes_final", "oct_w_final", "oct_a_final"]
     data = {k: np.load(os.path.join(out, k + ".npy")) for k in keep}
     for k in ("edge_idx", "edge_coord", "edge_pts", "edge_anchors"):         # 2048 of the 8192 draws are plenty
         data[k] = np.ascontiguousarray(data[k][:2048])

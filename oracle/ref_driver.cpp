@@ -263,6 +263,27 @@ int main(int argc, char** argv) {
                  n_rays, n_time, mf, ma, samples / n_time / n_rays, kept / n_time / n_rays, n_rays / (ma * 1e-3), mv);
     std::fclose(f);
   }
+  // ---- octree maintenance: ProcOctree / MarkInvisibleNodes on a deterministically damaged tree -------
+  if (full_grads) {
+    auto& oct = *sampler->pers_octree_;
+    const int n = (int)oct.tree_nodes_.size();
+    Tensor nodes_cpu = oct.tree_nodes_gpu_.to(torch::kCPU).clone();
+    TreeNode* tn = reinterpret_cast<TreeNode*>(nodes_cpu.data_ptr());
+    int k = 0;
+    for (int u = 0; u < n; u++)
+      if (tn[u].is_leaf_node && tn[u].trans_idx >= 0 && (k++ % 5 == 0)) tn[u].trans_idx = -1;     // as MarkInvalidNodes would
+    oct.tree_nodes_gpu_ = nodes_cpu.to(torch::kCUDA).contiguous();
+    oct.tree_visit_cnt_ = ((torch::arange(n, CUDAInt) * 7) % 11).to(torch::kInt32).contiguous();
+    dump("oct_nodes_in", oct.tree_nodes_gpu_); dump("oct_w_in", oct.tree_weight_stats_); dump("oct_a_in", oct.tree_alpha_stats_);
+    dump("oct_visit_in", oct.tree_visit_cnt_);
+    dump("oct_intri", oct.intri_.reshape({-1, 9})); dump("oct_w2c", oct.w2c_.reshape({-1, 12})); dump("oct_bound", oct.bound_);
+    oct.ProcOctree(true, true, false);
+    dump("oct_nodes_sub", oct.tree_nodes_gpu_); dump("oct_w_sub", oct.tree_weight_stats_); dump("oct_a_sub", oct.tree_alpha_stats_);
+    oct.MarkInvisibleNodes();
+    dump("oct_nodes_invis", oct.tree_nodes_gpu_);
+    oct.ProcOctree(true, false, false);
+    dump("oct_nodes_final", oct.tree_nodes_gpu_); dump("oct_w_final", oct.tree_weight_stats_); dump("oct_a_final", oct.tree_alpha_stats_);
+  }
   std::printf("ref_driver: done, dumps in %s\n", g_out.c_str());
   return 0;
 }

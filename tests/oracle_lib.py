@@ -219,5 +219,16 @@ def img2world_rays(poses, intri, dist_params, cam_indices, ij):
     return rays_o, rays_d
 
 
+def octree_proc(nodes, wstat, astat, visit, subdivide, brute_force=False):
+    """-> (nodes_out bytes [n_out*64], wstat_out, astat_out)"""
+    n = nodes.size // 64
+    out = np.zeros(9 * n * 64, np.uint8)
+    w, a = np.zeros(9 * n, np.int32), np.zeros(9 * n, np.int32)
+    lib().orc_octree_proc.restype = ctypes.c_int
+    m = lib().orc_octree_proc(_p(c(nodes, np.uint8)), _p(c(wstat, np.int32)), _p(c(astat, np.int32)), _p(c(visit, np.int32)),
+                              I(n), I(int(subdivide)), I(int(brute_force)), _p(out), _p(w), _p(a))
+    return out[:m * 64].copy(), w[:m].copy(), a[:m].copy()
+
+
 def num_threads():
     return int(lib().orc_num_threads())

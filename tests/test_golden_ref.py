@@ -131,3 +131,22 @@ def test_ray_generation_bit_exact_vs_reference(g, oracle):
     ro, rd = oracle.img2world_rays(g["ds_poses"], g["ds_intri"], g["ds_dist_params"], g["emb_idx"].astype(np.int32), g["ray_ij"])
     np.testing.assert_array_equal(bits(ro), bits(g["rays_o"]))
     np.testing.assert_array_equal(bits(rd), bits(g["rays_d"]))
+
+
+def _node_fields(blob):
+    t = np.ascontiguousarray(blob).view(np.uint8).reshape(-1, 64)             # drop the struct padding (never initialised)
+    return np.concatenate([t[:, :53], t[:, 56:60]], 1)
+
+
+def test_octree_maintenance_vs_reference(g, oracle):
+    """PersOctree::ProcOctree (PersSampler.cpp:120-330) on the reference's ngp_fox octree with every 5th valid leaf
+    killed: subdivision of the visited leaves, then compaction of the tree it marked invisible."""
+    if "oct_nodes_in" not in g:
+        pytest.skip("fixture predates the octree dump")
+    on, ow, oa = oracle.octree_proc(g["oct_nodes_in"], g["oct_w_in"], g["oct_a_in"], g["oct_visit_in"], True, False)
+    np.testing.assert_array_equal(_node_fields(on), _node_fields(g["oct_nodes_sub"]))
+    np.testing.assert_array_equal(ow, g["oct_w_sub"]); np.testing.assert_array_equal(oa, g["oct_a_sub"])
+    visit0 = np.zeros(g["oct_w_sub"].shape[0], np.int32)
+    on, ow, oa = oracle.octree_proc(g["oct_nodes_invis"], g["oct_w_sub"], g["oct_a_sub"], visit0, False, False)
+    np.testing.assert_array_equal(_node_fields(on), _node_fields(g["oct_nodes_final"]))
+    np.testing.assert_array_equal(ow, g["oct_w_final"]); np.testing.assert_array_equal(oa, g["oct_a_final"])

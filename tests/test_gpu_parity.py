@@ -622,3 +622,55 @@ def test_img2world_rays_and_gather_vs_oracle(oracle):
     np.testing.assert_array_equal(N(b), bounds[c])
     wo, wd = oracle.img2world_rays(poses, intri, dist, c.astype(np.int32), np.stack([i, j], -1).astype(np.int32))
     np.testing.assert_array_equal(N(rd).view(np.uint32), wd.view(np.uint32))
+
+
+# ---------------------------------------------------------------------- octree maintenance ----
+def _damage_tree(nodes_bytes, rng, frac):
+    """mark a random subset of the valid leaves dead (trans_idx = -1), like MarkInvalidNodes does over training"""
+    t = nodes_bytes.copy().view(np.int32).reshape(-1, 16)
+    is_leaf = nodes_bytes.reshape(-1, 64)[:, 52] != 0
+    leaves = np.nonzero(is_leaf & (t[:, 14] >= 0))[0]
+    dead = rng.choice(leaves, int(len(leaves) * frac), replace=False)
+    t[dead, 14] = -1
+    return t.reshape(-1).view(np.uint8), dead
+
+
+@pytest.mark.parametrize("frac", [0.0, 0.3, 0.8])
+def test_octree_proc_matches_oracle(scene, oracle, frac):
+    """f2b_octree_proc == the sequential ProcOctree restatement, byte for byte: compaction alone, subdivision of the
+    visited leaves, brute-force subdivision, and a second round on the result (deeper tree, collapsed chains)."""
+    from test_gpu_render import build
+    rng = np.random.default_rng(int(frac * 10) + 1)
+    gdp, sampler, field, shader, renderer = build(scene)
+    nodes, dead = _damage_tree(scene["nodes"], rng, frac)
+    n = nodes.size // 64
+    w = rng.integers(-100, 2000, n).astype(np.int32); a = rng.integers(-100, 2000, n).astype(np.int32)
+    visit = rng.integers(0, 12, n).astype(np.int32)
+    for subdivide, brute in ((False, False), (True, False), (True, True)):
+        sampler.tree_nodes_gpu_, sampler.tree_weight_stats_, sampler.tree_alpha_stats_ = T(nodes), T(w), T(a)
+        sampler.tree_visit_cnt_ = T(visit)
+        m = sampler.ProcOctree(True, subdivide, brute)
+        on, ow, oa = oracle.octree_proc(nodes, w, a, visit, subdivide, brute)
+        assert m == on.size // 64 and (frac == 0.0 or subdivide or m < n)
+        np.testing.assert_array_equal(N(sampler.tree_nodes_gpu_), on)
+        np.testing.assert_array_equal(N(sampler.tree_weight_stats_), ow)
+        np.testing.assert_array_equal(N(sampler.tree_alpha_stats_), oa)
+        assert int(sampler.tree_visit_cnt_.abs().sum()) == 0 and sampler.tree_visit_cnt_.shape[0] == m
+        if subdivide and not brute:                                  # second round on the subdivided tree
+            n2, d2 = _damage_tree(on, rng, 0.5)
+            v2 = rng.integers(0, 12, m).astype(np.int32)
+            sampler.tree_nodes_gpu_, sampler.tree_visit_cnt_ = T(n2), T(v2)
+            m2 = sampler.ProcOctree(True, True, False)
+            on2, ow2, oa2 = oracle.octree_proc(n2, ow, oa, v2, True, False)
+            assert m2 == on2.size // 64
+            np.testing.assert_array_equal(N(sampler.tree_nodes_gpu_), on2)
+            np.testing.assert_array_equal(N(sampler.tree_weight_stats_), ow2)
+    # the maintained tree still renders: march it
+    o, d, dn, cam = make_rays_for(scene, 64)
+    sr = sampler.GetSamples(T(o), T(d))
+    assert sr.pts.shape[0] > 0 and int(sr.anchors[:, 1].max()) < sampler.n_nodes
+
+
+def make_rays_for(scene, n):
+    from conftest import make_rays
+    return make_rays(scene, n, seed=3)

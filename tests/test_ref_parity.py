@@ -279,3 +279,38 @@ def test_ray_generation_vs_reference(ref):
     np.testing.assert_array_equal(N(d2).view(np.uint32), ref["rays_d"].view(np.uint32))
     json.dump(dict(dist_params_abs_max=float(np.abs(ref["ds_dist_params"]).max()), n_rays=int(N_RAYS)),
               open(os.path.join(ROOT, "gpurun_out", "ref_rays.json"), "w"))
+
+
+def _node_fields(blob):
+    """TreeNode blob -> the meaningful fields only (the reference never initialises the struct padding)."""
+    t = np.ascontiguousarray(blob).view(np.uint8).reshape(-1, 64)
+    return np.concatenate([t[:, :53], t[:, 56:60]], 1)
+
+
+def test_octree_maintenance_vs_reference(ref, oracle):
+    """the device ProcOctree / MarkInvisibleNodes against the reference's own host pass on its ngp_fox octree
+    (every 5th valid leaf killed, synthetic visit counts): subdivide -> mark invisible -> compact, byte-identical blobs."""
+    if "oct_nodes_in" not in ref:
+        pytest.skip("ref_driver without the octree dump")
+    gdp, sampler, field, shader, renderer = build_from_ref(ref)
+    sampler.tree_nodes_gpu_, sampler.tree_weight_stats_ = T(ref["oct_nodes_in"]), T(ref["oct_w_in"])
+    sampler.tree_alpha_stats_, sampler.tree_visit_cnt_ = T(ref["oct_a_in"]), T(ref["oct_visit_in"])
+    on, ow, oa = oracle.octree_proc(ref["oct_nodes_in"], ref["oct_w_in"], ref["oct_a_in"], ref["oct_visit_in"], True, False)
+    np.testing.assert_array_equal(_node_fields(on), _node_fields(ref["oct_nodes_sub"]))    # the sequential restatement first
+    m = sampler.ProcOctree(True, True, False)
+    assert m == ref["oct_nodes_sub"].size // 64
+    np.testing.assert_array_equal(_node_fields(N(sampler.tree_nodes_gpu_)), _node_fields(ref["oct_nodes_sub"]))
+    np.testing.assert_array_equal(N(sampler.tree_weight_stats_), ref["oct_w_sub"])
+    np.testing.assert_array_equal(N(sampler.tree_alpha_stats_), ref["oct_a_sub"])
+    sampler.MarkInvisibleNodes(ref["oct_intri"].reshape(-1, 3, 3), ref["oct_w2c"].reshape(-1, 3, 4), ref["oct_bound"])
+    mine = N(sampler.tree_nodes_gpu_).view(np.int32).reshape(-1, 16)[:, 14]
+    theirs = ref["oct_nodes_invis"].view(np.int32).reshape(-1, 16)[:, 14]
+    flips = int(((mine < 0) != (theirs < 0)).sum())
+    json.dump(dict(nodes=int(m), invisible_ref=int((theirs < 0).sum()), invisible_ours=int((mine < 0).sum()), flips=flips),
+              open(os.path.join(ROOT, "gpurun_out", "ref_octree.json"), "w"))
+    assert flips <= max(1, m // 2000), flips                                     # fp32 visibility tests: borderline nodes only
+    sampler.tree_nodes_gpu_ = T(ref["oct_nodes_invis"])                          # continue from the reference's own marks
+    m = sampler.ProcOctree(True, False, False)
+    np.testing.assert_array_equal(_node_fields(N(sampler.tree_nodes_gpu_)), _node_fields(ref["oct_nodes_final"]))
+    np.testing.assert_array_equal(N(sampler.tree_weight_stats_), ref["oct_w_final"])
+    np.testing.assert_array_equal(N(sampler.tree_alpha_stats_), ref["oct_a_final"])
