@@ -168,7 +168,12 @@ composite_fwd_kernel(const float* __restrict__ logit, int logit_stride, const fl
   const int lane = threadIdx.x & 31;
   if (ray >= n_rays) return;
   const int beg = bounds[2 * ray], end = bounds[2 * ray + 1];
-  float run = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, sd = 0.f, sz = 0.f;
+  // The five per-ray sums (FlexOps::Sum: serial left-to-right per ray, FlexOps.cu:5-30) are independent serial chains:
+  // lanes 0..4 each own one and walk the chunk's 32 addends out of shared memory (32 LDS + 32 FADD for all five
+  // together) instead of five 32-step shuffle chains executed by every lane — same additions in the same order.
+  __shared__ float s_add[8][5][32];
+  float (*sa)[32] = s_add[threadIdx.x >> 5];
+  float run = 0.f, acc5 = 0.f;                                  // acc5: lane c < 5 holds sum c (r, g, b, w/t, w*t)
   for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
     const bool valid = i < end;
@@ -184,12 +189,17 @@ composite_fwd_kernel(const float* __restrict__ logit, int logit_stride, const fl
     const float acc = chain_excl(tau, run, nv, lane);
     const float w = fmul(expf(-acc), alpha);
     if (valid) weights[i] = w;
-    chain_sum(fmul(w, r), cr, nv);
-    chain_sum(fmul(w, g), cg, nv);
-    chain_sum(fmul(w, b), cb, nv);
-    chain_sum(fdiv(w, ts), sd, nv);
-    chain_sum(fmul(w, ts), sz, nv);
+    sa[0][lane] = fmul(w, r); sa[1][lane] = fmul(w, g); sa[2][lane] = fmul(w, b);
+    sa[3][lane] = fdiv(w, ts); sa[4][lane] = fmul(w, ts);
+    __syncwarp();
+    if (lane < 5) {
+      const float* mine = sa[lane];
+      for (int j = 0; j < nv; j++) acc5 = fadd(acc5, mine[j]);
+    }
+    __syncwarp();
   }
+  const float cr = __shfl_sync(kFull, acc5, 0), cg = __shfl_sync(kFull, acc5, 1), cb = __shfl_sync(kFull, acc5, 2);
+  const float sd = __shfl_sync(kFull, acc5, 3), sz = __shfl_sync(kFull, acc5, 4);
   if (lane == 0) {
     const float lt = expf(-run);                              // last_trans = exp(-Sum(sec_density))
     colors[ray * 3 + 0] = fadd(cr, fmul(lt, bg[ray * 3 + 0]));
