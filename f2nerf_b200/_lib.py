@@ -85,6 +85,7 @@ SIGNATURES = {
     "f2b_compact_samples": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "f2b_composite_fwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "f2b_composite_bwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, _P],
+    "f2b_composite_act_bwd": [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_float, _P, c_int, _P, _P],
     "f2b_flex_sum": [_P, c_int, _P, c_int, _P, _P],
     "f2b_flex_accumulate_sum": [_P, _P, c_int, c_int, _P, _P],
     "f2b_weight_var_fwd": [_P, _P, c_int, _P, _P],

@@ -15,6 +15,7 @@
 // FlexAccumulateSumForwardKernel / FlexSumForwardKernel do.  Backward uses ordinary warp scans.
 #include "common.cuh"
 #include "scan.cuh"
+#include "shader.cuh"
 
 namespace f2b {
 
@@ -213,6 +214,7 @@ composite_fwd_kernel(const float* __restrict__ logit, int logit_stride, const fl
 // ---- backward composite -----------------------------------------------------------------------
 // sweep 1 (front to back): exclusive optical depth A_i (serial order, parked in d_logit), S, Zs.
 // sweep 2 (back to front): per-sample gradients with a reverse warp scan for sum_{k>i} dA_k.
+template <bool FUSE_ACT>
 __global__ void __launch_bounds__(256)
 composite_bwd_kernel(const float* __restrict__ logit, int logit_stride, const float* __restrict__ rgb,
                      const float* __restrict__ dt, const float* __restrict__ t,
@@ -220,7 +222,10 @@ composite_bwd_kernel(const float* __restrict__ logit, int logit_stride, const fl
                      const float* __restrict__ d_colors, const float* __restrict__ d_disp,
                      const float* __restrict__ d_depth, const float* __restrict__ d_weights,
                      float gs_progress, float* __restrict__ d_logit, int dlogit_stride,
-                     float* __restrict__ d_rgb) {
+                     float* __restrict__ d_rgb, const __half* __restrict__ raw, __half* __restrict__ d_raw,
+                     float act_loss_scale) {
+  // FUSE_ACT: the colour gradient goes straight through the scaled sigmoid's backward (SHShader.cpp:27-28) into the
+  // shader MLP's fp16 dL/dout row [g_r, g_g, g_b, 0 x 13] * loss_scale instead of being written as fp32 d_rgb.
   const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ray >= n_rays) return;
@@ -295,9 +300,22 @@ composite_bwd_kernel(const float* __restrict__ logit, int logit_stride, const fl
       const float ddens = dtau * dtv * scale;
       // TruncExp backward: g * exp(clamp(x, -100, 5))   (CustomOps.cpp:16-18)
       d_logit[size_t(i) * dlogit_stride] = ddens * expf(fminf(fmaxf(x, -100.f), 5.f));
-      d_rgb[size_t(i) * 3 + 0] = w * dcr * scale;
-      d_rgb[size_t(i) * 3 + 1] = w * dcg * scale;
-      d_rgb[size_t(i) * 3 + 2] = w * dcb * scale;
+      const float gr = w * dcr * scale, gg = w * dcg * scale, gb = w * dcb * scale;
+      if (FUSE_ACT) {
+        const uint2 rw = __ldg(reinterpret_cast<const uint2*>(raw + size_t(i) * 16));
+        const float2 o01 = __half22float2(*reinterpret_cast<const __half2*>(&rw.x));
+        const float2 o2x = __half22float2(*reinterpret_cast<const __half2*>(&rw.y));
+        const __half2 h0 = __floats2half2_rn(shade_act_bwd(o01.x, gr, act_loss_scale), shade_act_bwd(o01.y, gg, act_loss_scale));
+        const __half2 h1 = __floats2half2_rn(shade_act_bwd(o2x.x, gb, act_loss_scale), 0.f);
+        uint4 v0 = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1), 0u, 0u);
+        uint4* dst = reinterpret_cast<uint4*>(d_raw + size_t(i) * 16);
+        dst[0] = v0;
+        dst[1] = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        d_rgb[size_t(i) * 3 + 0] = gr;
+        d_rgb[size_t(i) * 3 + 1] = gg;
+        d_rgb[size_t(i) * 3 + 2] = gb;
+      }
     }
   }
 }
@@ -465,10 +483,24 @@ extern "C" int f2b_composite_bwd(const float* logit, int logit_stride, const flo
   if (n_rays <= 0) return F2B_OK;
   F2B_REQUIRE(logit && rgb && dt && t && pts_idx_bounds && bg_color && d_colors && d_logit && d_rgb,
               "f2b_composite_bwd: null pointer");
-  composite_bwd_kernel<<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(
+  composite_bwd_kernel<false><<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(
       logit, logit_stride, rgb, dt, t, pts_idx_bounds, bg_color, n_rays, d_colors, d_disparity, d_depth, d_weights,
-      grad_scaling_progress, d_logit, dlogit_stride, d_rgb);
+      grad_scaling_progress, d_logit, dlogit_stride, d_rgb, nullptr, nullptr, 0.f);
   return check_launch("f2b_composite_bwd");
+}
+
+extern "C" int f2b_composite_act_bwd(const float* logit, int logit_stride, const float* rgb, const float* dt,
+                                     const float* t, const int* pts_idx_bounds, const float* bg_color, int n_rays,
+                                     const float* d_colors, const float* d_disparity, const float* d_depth,
+                                     const float* d_weights, float grad_scaling_progress, const void* raw_f16,
+                                     float loss_scale, float* d_logit, int dlogit_stride, void* d_raw_f16, void* stream) {
+  if (n_rays <= 0) return F2B_OK;
+  F2B_REQUIRE(logit && rgb && dt && t && pts_idx_bounds && bg_color && d_colors && d_logit && raw_f16 && d_raw_f16,
+              "f2b_composite_act_bwd: null pointer");
+  composite_bwd_kernel<true><<<warp_grid(n_rays), 256, 0, as_stream(stream)>>>(
+      logit, logit_stride, rgb, dt, t, pts_idx_bounds, bg_color, n_rays, d_colors, d_disparity, d_depth, d_weights,
+      grad_scaling_progress, d_logit, dlogit_stride, nullptr, (const __half*)raw_f16, (__half*)d_raw_f16, loss_scale);
+  return check_launch("f2b_composite_act_bwd");
 }
 
 extern "C" int f2b_flex_sum(const float* val, int vec, const int* idx_start_end, int n_outs, float* sum, void* stream) {

@@ -62,17 +62,12 @@ __global__ void shader_act_bwd_kernel(const __half* __restrict__ raw, const floa
                                       float loss_scale, __half* __restrict__ d_raw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float c = 1.f + 2.f * 1e-3f;
   __half2 h[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) h[k] = __floats2half2_rn(0.f, 0.f);
   float g[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const float o = __half2float(raw[size_t(i) * 16 + k]);
-    const float s = 1.f / (1.f + expf(-o));
-    g[k] = d_rgb[size_t(i) * 3 + k] * c * s * (1.f - s) * loss_scale;
-  }
+  for (int k = 0; k < 3; k++) g[k] = shade_act_bwd(__half2float(raw[size_t(i) * 16 + k]), d_rgb[size_t(i) * 3 + k], loss_scale);
   h[0] = __floats2half2_rn(g[0], g[1]);
   h[1] = __floats2half2_rn(g[2], 0.f);
   uint4* dst = reinterpret_cast<uint4*>(d_raw + size_t(i) * 16);

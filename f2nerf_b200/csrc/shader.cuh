@@ -62,4 +62,11 @@ __device__ __forceinline__ float shade_act(float o) {
   return fsub(fdiv(c, fadd(1.f, expf(-o))), eps);
 }
 
+// backward of shade_act for one channel: loss_scale * d_rgb * (1 + 2e-3) * sigmoid'(o)   (fp32, rounded to fp16 by the caller)
+__device__ __forceinline__ float shade_act_bwd(float o, float d_rgb, float loss_scale) {
+  const float c = 1.f + 2.f * 1e-3f;
+  const float s = fdiv(1.f, fadd(1.f, expf(-o)));
+  return fmul(fmul(fmul(fmul(d_rgb, c), s), fsub(1.f, s)), loss_scale);
+}
+
 }  // namespace f2b

@@ -306,7 +306,6 @@ class _RenderFunction(torch.autograd.Function):
         nh_s, nh_f = shader.mlp_.n_hidden_matmuls, field.mlp_.n_hidden_matmuls
         f16 = lambda *sh: torch.empty(sh, dtype=torch.float16, device=dev)
         d_logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
-        d_rgb = torch.empty((n_kept, 3), dtype=torch.float32, device=dev)
         d_raw, d_in16, d_scene16, dfeat16 = f16(n_kept, 16), f16(n_kept, 32), f16(n_q, 16), f16(n_q, 32)
         d_sparams, d_fparams = zeros(sparams16.numel()), zeros(fparams16.numel())
         d_table = torch.zeros_like(field.feat_pool_)
@@ -332,10 +331,10 @@ class _RenderFunction(torch.autograd.Function):
             if s1 <= s0:
                 continue
             nr, ns = r1 - r0, s1 - s0
-            call("f2b_composite_bwd", scene_feat[0], int(scene_feat[1]), rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr, d_colors[r0:r1],
-                 None if d_disp is None else d_disp[r0:r1], None if d_depth is None else d_depth[r0:r1], d_weights,
-                 float(ctx.gs_progress), d_logit, 1, d_rgb, stream())
-            call("f2b_shader_act_bwd", raw[s0:s1], d_rgb[s0:s1], ns, float(s_scale), d_raw[s0:s1], stream())
+            # composite backward with the colour activation's backward applied on the way out (fp16 d_raw directly)
+            call("f2b_composite_act_bwd", scene_feat[0], int(scene_feat[1]), rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr,
+                 d_colors[r0:r1], None if d_disp is None else d_disp[r0:r1], None if d_depth is None else d_depth[r0:r1],
+                 d_weights, float(ctx.gs_progress), raw, float(s_scale), d_logit, 1, d_raw, stream())
             call("f2b_mlp_bwd2", d_raw[s0:s1], mlp_in[s0:s1], s_hidden[0, s0:s1], s_hidden[1, s0:s1] if nh_s else None,
                  sparams16, int(nh_s), ns, d_in16[s0:s1], d_sparams, stream())
             ops.shader_prep_bwd_f16(d_in16, d_logit, bounds[r0:r1], None if ray_emb_idx is None else ray_emb_idx[r0:r1],

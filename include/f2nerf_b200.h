@@ -312,6 +312,13 @@ int f2b_composite_bwd(const float* logit, int logit_stride, const float* rgb, co
                       const float* d_colors, const float* d_disparity, const float* d_depth,
                       const float* d_weights, float grad_scaling_progress,
                       float* d_logit, int dlogit_stride, float* d_rgb, void* stream);
+/* f2b_composite_bwd with the colour activation's backward (f2b_shader_act_bwd) applied on the way out: instead of
+ * d_rgb [P,3] fp32 it writes the shader MLP's dL/dout row d_raw [P,16] fp16 = loss_scale * d_rgb * sigmoid'(raw), 0 x 13. */
+int f2b_composite_act_bwd(const float* logit, int logit_stride, const float* rgb, const float* dt, const float* t,
+                          const int* pts_idx_bounds, const float* bg_color, int n_rays, const float* d_colors,
+                          const float* d_disparity, const float* d_depth, const float* d_weights,
+                          float grad_scaling_progress, const void* raw_f16 /* [P,16] */, float loss_scale,
+                          float* d_logit, int dlogit_stride, void* d_raw_f16 /* [P,16] */, void* stream);
 /* Stand-alone FlexOps (FlexOps.h:15-16) for callers that use them directly. */
 int f2b_flex_sum(const float* val, int vec, const int* idx_start_end, int n_outs, float* sum, void* stream);
 int f2b_flex_accumulate_sum(const float* val, const int* idx_start_end, int n_outs, int include_this,

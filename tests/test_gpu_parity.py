@@ -524,6 +524,29 @@ def test_octree_votes_bit_exact(scene, oracle):
     assert (nodes_ref != scene["nodes"]).any(), "test inputs must prune at least one node"
 
 
+def test_composite_act_bwd_matches_two_step(scene, oracle):
+    """f2b_composite_act_bwd == f2b_composite_bwd followed by f2b_shader_act_bwd, bit for bit."""
+    from f2nerf_b200 import ops
+    from f2nerf_b200._lib import call, stream
+    smp, feat, _, bg_np = composite_inputs(scene, oracle)
+    P, R = smp["dt"].shape[0], smp["bounds"].shape[0]
+    rng = np.random.default_rng(77)
+    raw = T((rng.standard_normal((P, 16)) * 2).astype(np.float16))
+    rgb = ops.shader_act(raw)
+    logit, dt, t, bounds, bg = T(np.ascontiguousarray(feat[:, 0])), T(smp["dt"]), T(smp["t"]), T(smp["bounds"]), T(bg_np)
+    d_colors = T(rng.standard_normal((R, 3)).astype(np.float32)); d_disp = T(rng.standard_normal(R).astype(np.float32))
+    d_w = T((rng.standard_normal(P) * 1e-2).astype(np.float32))
+    for gs in (1.0, 0.3):
+        d_logit0 = torch.empty(P, device=DEV)
+        d_rgb = ops.composite_bwd(logit, 1, rgb, dt, t, bounds, bg, d_colors, d_disp, None, d_w, gs, d_logit0, 1)
+        want = ops.shader_act_bwd(raw, d_rgb, 128.0)
+        d_logit1 = torch.empty(P, device=DEV); d_raw = torch.empty((P, 16), dtype=torch.float16, device=DEV)
+        call("f2b_composite_act_bwd", logit, 1, rgb, dt, t, bounds, bg, R, d_colors, d_disp, None, d_w, float(gs), raw, 128.0,
+             d_logit1, 1, d_raw, stream())
+        np.testing.assert_array_equal(N(d_logit1), N(d_logit0))
+        np.testing.assert_array_equal(N(d_raw).view(np.uint16), N(want).view(np.uint16))
+
+
 # ---------------------------------------------------------------------- optimizer (SURVEY 8f N1) ----
 def aten_adam_step(p, g, m, v, step, lr, b1, b2, eps, wd):
     """torch::optim::Adam::step of the C++ frontend (torch/csrc/api/src/optim/adam.cpp), op for op: the very ATen
