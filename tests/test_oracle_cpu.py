@@ -199,3 +199,92 @@ def test_scene_builder_is_consistent(scene):
             if c >= 0:
                 assert nodes[c]["parent"] >= 0 and abs(nodes[c]["side_len"] * 2 - n["side_len"]) < 1e-6
     assert (edges["t_idx_a"] < len(trans)).all() and (edges["t_idx_b"] < len(trans)).all()
+
+
+def _tree(blob):
+    t = np.ascontiguousarray(blob).view(np.uint8).reshape(-1, 64)
+    i = t.view(np.int32)
+    return dict(center=t.view(np.float32)[:, :3], side=t.view(np.float32)[:, 3], parent=i[:, 4], childs=i[:, 5:13],
+                leaf=t[:, 52] != 0, trans=i[:, 14])
+
+
+def test_octree_proc_invariants(scene, oracle):
+    """ProcOctree restatement on the synthetic octree with random dead leaves: structural invariants of the
+    result (links consistent, no dead leaf / single-child chain left, pre-order numbering, children geometry, stats)."""
+    rng = np.random.default_rng(3)
+    nodes = scene["nodes"].copy()
+    t = _tree(nodes)
+    live = np.nonzero(t["leaf"] & (t["trans"] >= 0))[0]
+    kill = rng.choice(live, len(live) // 3, replace=False)
+    nodes.view(np.int32).reshape(-1, 16)[kill, 14] = -1
+    n = nodes.size // 64
+    w, a = rng.integers(-50, 3000, n).astype(np.int32), rng.integers(-50, 3000, n).astype(np.int32)
+    visit = rng.integers(0, 10, n).astype(np.int32)
+    for subdivide in (False, True):
+        on, ow, oa = oracle.octree_proc(nodes, w, a, visit, subdivide)
+        o = _tree(on)
+        m = o["parent"].shape[0]
+        assert o["parent"][0] == -1 and (o["parent"][1:] >= 0).all() and (o["parent"][1:] < np.arange(1, m)).all()
+        for u in range(m):
+            ch = o["childs"][u][o["childs"][u] >= 0]
+            assert (o["parent"][ch] == u).all()
+            if o["leaf"][u]:
+                assert len(ch) == 0 and o["trans"][u] >= 0                      # only live leaves survive
+            else:
+                assert o["trans"][u] < 0 and len(ch) >= (1 if u == 0 else 2)     # no single-child chains below the root
+        # pre-order: a node's first child follows it directly
+        if subdivide:
+            for u in range(m):
+                ch = o["childs"][u][o["childs"][u] >= 0]
+                if len(ch):
+                    assert ch[0] == u + 1 and (np.diff(ch) > 0).all()
+        t2 = _tree(nodes)                                                          # the damaged input tree
+        live_before = int((t2["leaf"] & (t2["trans"] >= 0)).sum())
+        n_live_after = int((o["leaf"]).sum())
+        if not subdivide:
+            assert n_live_after == live_before
+        else:                                                                      # each visited (> 4) live leaf -> 8 children
+            lv = np.nonzero(t2["leaf"] & (t2["trans"] >= 0))[0]
+            split = int((visit[lv] > 4).sum())
+            assert n_live_after == live_before + 7 * split
+            # children are the octants of their parent: centre +- side/4, half the side, parent's old trans_idx
+            for u in range(m):
+                ch = o["childs"][u]
+                if (ch >= 0).all() and o["leaf"][ch].all() and np.allclose(o["side"][ch], o["side"][u] / 2) and \
+                        len(set(o["trans"][ch])) == 1:
+                    off = (o["center"][ch] - o["center"][u]) / (o["side"][u] / 4)
+                    if np.allclose(np.abs(off), 1):
+                        want = np.array([[(st >> 2) & 1, (st >> 1) & 1, st & 1] for st in range(8)]) * 2 - 1
+                        np.testing.assert_array_equal(off, want)
+        assert ow.shape[0] == m and oa.shape[0] == m
+
+
+def test_img2world_rays_undistorted_closed_form(oracle):
+    """Ray generation restatement: with zero lens distortion the Newton iteration is a no-op and the ray is
+    R [ (j+.5-cx)/fx, -(i+.5-cy)/fy, -1 ]; with distortion, re-distorting the undistorted point returns the pixel."""
+    rng = np.random.default_rng(4)
+    n_cam, n = 3, 500
+    poses = rng.standard_normal((n_cam, 3, 4)).astype(np.float32)
+    intri = np.tile(np.array([[600., 0, 320.], [0, 610., 240.], [0, 0, 1]], np.float32), (n_cam, 1, 1))
+    cam = rng.integers(0, n_cam, n).astype(np.int32)
+    ij = np.stack([rng.integers(0, 480, n), rng.integers(0, 640, n)], -1).astype(np.int32)
+    ro, rd = oracle.img2world_rays(poses, intri, np.zeros((n_cam, 4), np.float32), cam, ij)
+    u = (ij[:, 1] + .5 - 320.) / 600.
+    v = (ij[:, 0] + .5 - 240.) / 610.
+    want = np.einsum("nij,nj->ni", poses[cam][:, :, :3].astype(np.float64), np.stack([u, -v, -np.ones(n)], -1))
+    np.testing.assert_allclose(rd, want, rtol=2e-6, atol=2e-6)
+    np.testing.assert_array_equal(ro, poses[cam][:, :, 3])
+    dist = np.tile(np.array([0.06, -0.08, -0.002, -0.0025], np.float32), (n_cam, 1))
+    ro2, rd2 = oracle.img2world_rays(poses, intri, dist, cam, ij)
+    # back to camera space, re-apply the distortion model (Dataset.cu:16-28): must land on the pixel's normalised coords
+    dcam = np.einsum("nji,nj->ni", poses[cam][:, :, :3].astype(np.float64), rd2.astype(np.float64))     # R^T d
+    if not np.allclose(np.abs(np.linalg.det(poses[cam][:, :, :3].astype(np.float64))), 1, atol=1e-3):
+        dcam = np.linalg.solve(poses[cam][:, :, :3].astype(np.float64), rd2.astype(np.float64)[..., None])[..., 0]
+    uu, vv = dcam[:, 0] / -dcam[:, 2], -dcam[:, 1] / -dcam[:, 2]
+    k1, k2, p1, p2 = (float(x) for x in dist[0])
+    r2 = uu * uu + vv * vv
+    radial = k1 * r2 + k2 * r2 * r2
+    du = uu * radial + 2 * p1 * uu * vv + p2 * (r2 + 2 * uu * uu)
+    dv = vv * radial + 2 * p2 * uu * vv + p1 * (r2 + 2 * vv * vv)
+    np.testing.assert_allclose(uu + du, u, atol=5e-5)
+    np.testing.assert_allclose(vv + dv, v, atol=5e-5)
