@@ -17,6 +17,9 @@
 #include <experimental/filesystem>
 #include <torch/torch.h>
 #include <cuda_runtime.h>
+#ifdef F2B_WITH_SHIM
+#include "../f2nerf_b200/shim/B200Ops.h"
+#endif
 #include "Common.h"
 #include "Utils/GlobalDataPool.h"
 #include "Utils/cnpy.h"
@@ -78,6 +81,28 @@ int main(int argc, char** argv) {
     field->mlp_->params_.data().mul_(4.f);          // wider density range so early stop triggers
     renderer->app_emb_.data().copy_((torch::rand({dataset->n_images_, 16}, g, CPUFloat) * .2f - .1f).to(torch::kCUDA));
   }
+
+#ifdef F2B_WITH_SHIM
+  // ---- ref_driver_b200 only: the operator-level drop-in.  The reference's OWN Renderer::Render / autograd / loss now drive
+  // the B200 subclasses: same octree object, same parameters, so every dump below is directly comparable
+  // with the pure-reference run of oracle/_ref/ref_driver.  Never built into ref_driver (the reference arm stays unmodified).
+  {
+    auto b_sampler = std::make_unique<B200Sampler>(gdp.get());
+    b_sampler->pers_octree_ = std::move(sampler->pers_octree_);          // the very same octree / warps / edge pool
+    auto b_field = std::make_unique<B200HashField>(gdp.get());
+    b_field->LoadStates(field->States(), 0);
+    auto b_shader = std::make_unique<B200Shader>(gdp.get());
+    b_shader->LoadStates(shader->States(), 0);
+    renderer->pts_sampler_ = std::move(b_sampler);
+    renderer->scene_field_ = std::move(b_field);
+    renderer->shader_ = std::move(b_shader);
+    sampler = dynamic_cast<PersSampler*>(renderer->pts_sampler_.get());
+    field = dynamic_cast<Hash3DAnchored*>(renderer->scene_field_.get());
+    shader = dynamic_cast<SHShader*>(renderer->shader_.get());
+    CHECK(sampler && field && shader);
+    std::printf("ref_driver_b200: PersSampler / Hash3DAnchored / SHShader replaced by the B200 subclasses\n");
+  }
+#endif
 
   // ---- scene blobs & scalars --------------------------------------------------------------------
   dump("tree_nodes", sampler->pers_octree_->tree_nodes_gpu_);
