@@ -288,3 +288,71 @@ def test_img2world_rays_undistorted_closed_form(oracle):
     dv = vv * radial + 2 * p2 * uu * vv + p1 * (r2 + 2 * vv * vv)
     np.testing.assert_allclose(uu + du, u, atol=5e-5)
     np.testing.assert_allclose(vv + dv, v, atol=5e-5)
+
+
+# ---- edge cases the reference's own flow produces: rays that hit nothing, zero rays, ragged / empty segments ---------------
+def test_sampler_rays_that_miss_the_scene(scene, oracle):
+    """A ray starting far outside and pointing away crosses no leaf: empty [s,s) bounds, first_oct_dis stays at its
+    1e9 sentinel (PersSampler.cu:374), neighbours are unaffected (mixed with hitting rays, as in a training batch)."""
+    o, d, dn, _ = make_rays(scene, 8)
+    o2, dn2 = o.copy(), dn.copy()
+    o2[[2, 5]] = np.float32([1e4, 1e4, 1e4]); dn2[[2, 5]] = np.float32([0.57735026, 0.57735026, 0.57735026])
+    noise = np.ones(1024 + 8 + 10, np.float32)
+    full = oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, 1 / 256, False, 1024)
+    s = oracle.sampler(scene["nodes"], scene["trans"], o2, dn2, noise, 0.05, 1e8, 1 / 256, False, 1024)
+    b, bf = s["bounds"], full["bounds"]
+    for r in (2, 5):
+        assert b[r, 0] == b[r, 1]
+        assert s["first_oct_dis"][r, 0] >= 1e8
+    for r in (0, 1, 3, 4, 6, 7):                                          # same samples as in the all-hitting batch
+        assert b[r, 1] - b[r, 0] == bf[r, 1] - bf[r, 0]
+        np.testing.assert_array_equal(s["pts"][b[r, 0]:b[r, 1]], full["pts"][bf[r, 0]:bf[r, 1]])
+        np.testing.assert_array_equal(s["anchors"][b[r, 0]:b[r, 1]], full["anchors"][bf[r, 0]:bf[r, 1]])
+    assert b[-1, 1] == s["pts"].shape[0]
+
+
+def test_sampler_zero_rays(scene, oracle):
+    z3 = np.zeros((0, 3), np.float32)
+    s = oracle.sampler(scene["nodes"], scene["trans"], z3, z3, np.ones(1034, np.float32), 0.05, 1e8, 1 / 256, False, 1024)
+    assert s["bounds"].shape == (0, 2) and s["pts"].shape[0] == 0 and s["t"].shape[0] == 0
+
+
+def test_composite_and_flex_ops_on_ragged_and_empty_segments(oracle):
+    """Segments of length 0, 1 and many in one batch: an empty ray renders the background with zero disparity / depth
+    (Renderer.cpp:205-218 with nothing accumulated), FlexOps sums over [s,s) are 0 (FlexOps.cu:24-47)."""
+    rng = np.random.default_rng(3)
+    lens = np.array([0, 1, 7, 0, 130, 1, 0], np.int32)
+    ends = np.cumsum(lens).astype(np.int32)
+    bounds = np.stack([ends - lens, ends], 1).astype(np.int32)
+    P, R = int(ends[-1]), len(lens)
+    logit = rng.normal(size=P).astype(np.float32) * 2
+    rgb = rng.random((P, 3), dtype=np.float32)
+    dt = (rng.random(P, dtype=np.float32) * .01 + .001).astype(np.float32)
+    t = np.concatenate([np.cumsum(dt[s:e]) + .1 for s, e in bounds]).astype(np.float32) if P else np.zeros(0, np.float32)
+    bg = rng.random((R, 3), dtype=np.float32)
+    colors, disp, depth, w = oracle.composite_fwd(logit, 1, rgb, dt, t, bounds, bg)
+    for r in np.flatnonzero(lens == 0):
+        np.testing.assert_array_equal(colors[r], bg[r])
+        assert disp[r] == 0 and depth[r] == 0
+    # independent float64 statement per ray
+    for r, (s, e) in enumerate(bounds):
+        sig = np.exp(logit[s:e].astype(np.float64) - 3.)                  # TruncExp(x - 3): the oracle's density activation
+        a = 1 - np.exp(-sig * dt[s:e])
+        T = np.concatenate([[1.], np.cumprod(1 - a)[:-1]]) if e > s else np.zeros(0)
+        ww = a * T
+        np.testing.assert_allclose(w[s:e], ww, rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(colors[r], (ww[:, None] * rgb[s:e]).sum(0) + (1 - ww.sum()) * bg[r], rtol=2e-5, atol=2e-6)
+    fs = oracle.flex_sum(w, bounds)
+    assert (fs[lens == 0] == 0).all()
+    np.testing.assert_allclose(fs, [w[s:e].astype(np.float64).sum() for s, e in bounds], rtol=1e-5, atol=1e-7)
+    acc = oracle.flex_accumulate(w, bounds, False)                      # exclusive prefix inside each segment
+    for s, e in bounds:
+        if e > s:
+            assert acc[s] == 0
+            np.testing.assert_allclose(acc[s:e], np.concatenate([[0.], np.cumsum(w[s:e].astype(np.float64))[:-1]]), rtol=1e-5, atol=1e-7)
+    # early stop and the bound filter keep segment order and emptiness
+    ww, aa, keep, nb, tot = oracle.early_stop(logit, 1, dt, bounds)
+    nb2, tot2 = oracle.filter_bounds(keep, bounds)
+    np.testing.assert_array_equal(nb, nb2)
+    assert tot == tot2 == int(keep.sum()) and nb[-1, 1] == tot
+    assert ((nb[:, 1] - nb[:, 0]) == [int(keep[s:e].sum()) for s, e in bounds]).all()
