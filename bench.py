@@ -4,12 +4,18 @@
 One "step" = one pass of the hot path over one batch: Renderer.Render (perspective-warp ray march,
 early-stop pass, hash encode, density + colour MLPs, composite) + the trainer's loss + backward down
 to the parameter gradients (+ the NCCL gradient / octree-vote all-reduce when N > 1).  The optimizer
-step is outside the path.  Workload: BASELINE.json configs[1] shape — 4096 rays x
-<= 1024 samples per ray per GPU, log2_table_size 19, wanjinyou.yaml sampler settings — on a synthetic
-scene (the reference dataset does not travel to the GPU box), random-init table / MLPs.
+step is outside the path.
 
-  python bench.py --gpus N --steps K --warmup W            (torchrun launches N > 1)
-  python bench.py --impl reference ...                      CPU port of the path (oracle), rank 0 only
+Workload (``--config``, default ``wanjinyou`` = BASELINE.json configs[1], the configuration the metric is quoted on):
+4096 rays x <= 1024 samples per ray per GPU, log2_table_size 19, confs/wanjinyou.yaml sampler settings, on the
+REFERENCE'S OWN ngp_fox octree / warps / cameras (committed fixture tests/golden/ref_ngp_fox.npz — the blobs the
+unmodified reference built), rays drawn like Dataset::RandRaysData under seed 2023, parameters initialised like
+oracle/ref_driver.cpp — so `reference_gpu` (the compiled reference, oracle/_ref/ref_driver, timed on the same box)
+runs the very same batch.  Other configs (tests/workloads.py): free, nerf360 (8192 rays global, strong scaling),
+big20, big22, synthetic.
+
+  python bench.py --gpus N --steps K --warmup W [--config C]      (torchrun launches N > 1)
+  python bench.py --impl reference ...     the path's CPU port (oracle/) on the same config, all host threads, rank 0 only
 """
 import argparse
 import json
@@ -25,11 +31,23 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-N_RAYS = 4096
-SAMPLE_L = 1.0 / 256
-NEAR = 0.01
-SCALE_BY_DIS = True
-LOG2_TABLE = 19
+import workloads as W  # noqa: E402   (numpy / torch-CPU only: does not load the CUDA library)
+
+
+def config_dict(args, world):
+    """The `config` object of the JSON line: a pure function of (--config, --rays, N) so both arms print the same one."""
+    cfg = W.CONFIGS[args.config]
+    rays = args.rays or cfg["rays"]
+    per_gpu = rays // world if cfg["scaling"] == "strong" else rays
+    scene = ("the reference's ngp_fox octree / warps / cameras (tests/golden/ref_ngp_fox.npz), rays as Dataset::RandRaysData seed 2023"
+             if cfg["scene"] == "ngp_fox" else "synthetic 24-camera octree (tests/synth_scene.py)")
+    return {"workload": f"{args.config}: BASELINE configs[{cfg['baseline_config']}] ({cfg['yaml']}) — {per_gpu} rays x <=1024 samples per GPU, "
+                        f"near {cfg['near']}, scale_by_dis {cfg['scale_by_dis']}, use_app_emb {cfg['use_app_emb']}, sample_l 1/256, "
+                        f"fineness 1, log2_table_size {cfg['log2_table']}; {scene}; table U(-1,1), field MLP x4 (as oracle/ref_driver.cpp); "
+                        "Render + loss + backward",
+            "name": args.config, "rays_per_gpu": per_gpu, "global_rays": per_gpu * world, "log2_table_size": cfg["log2_table"],
+            "parallelism": f"dp{world} (rays sharded, params replicated)",
+            "l2": "per-step working set (>=100 MB of samples + the table) exceeds the 126 MB L2; no explicit flush"}
 
 
 def load_peaks():
@@ -83,25 +101,46 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows)}
 
 
-def build_problem(rank, n_rays, log2_table, device):
+def build_problem(rank, world, args, device):
     import torch
-    from f2nerf_b200 import TRAIN, GlobalDataPool, Hash3DAnchored, PersSampler, Renderer, SHShader
-    from f2nerf_b200.scene import SyntheticScene
-    sc = SyntheticScene(n_cams=24, seed=0)                       # identical octree on every rank
-    nodes, trans, edges = sc.blobs()
+    from f2nerf_b200 import TRAIN, GlobalDataPool, Hash3DAnchored, PersSampler, RayGenerator, Renderer, SHShader
+    cfg = W.CONFIGS[args.config]
+    sb = W.scene_blobs(args.config)                               # identical octree on every rank
+    nodes, trans, edges = sb["nodes"], sb["trans"], sb["edges"]
     gdp = GlobalDataPool()
-    torch.manual_seed(2022)                                       # replicated parameters
-    sampler = PersSampler(gdp, nodes, trans, edges, near=NEAR, sample_l=SAMPLE_L, scale_by_dis=SCALE_BY_DIS, device=device)
-    field = Hash3DAnchored(gdp, log2_table_size=log2_table, device=device)
-    field.Reset()
+    sampler = PersSampler(gdp, nodes, trans, edges, near=cfg["near"], sample_l=cfg["sample_l"], scale_by_dis=cfg["scale_by_dis"],
+                          device=device)
+    par = W.init_params(args.config, gdp.n_volumes_, sb["n_images"], sb["prim"], sb["bias"])       # replicated parameters
+    field = Hash3DAnchored(gdp, log2_table_size=cfg["log2_table"], device=device, prim_pool=par["prim"], bias_pool=par["bias"])
+    field.feat_pool_.data.copy_(torch.from_numpy(par["table"]))
+    field.mlp_.params_.data.copy_(torch.from_numpy(par["field_mlp"]))
     shader = SHShader(gdp, device=device)
-    renderer = Renderer(gdp, sampler, field, shader, n_images=len(sc.c2w), use_app_emb=True, device=device)
+    shader.mlp_.params_.data.copy_(torch.from_numpy(par["shader_mlp"]))
+    renderer = Renderer(gdp, sampler, field, shader, n_images=sb["n_images"], use_app_emb=cfg["use_app_emb"], device=device)
+    renderer.app_emb_.data.copy_(torch.from_numpy(par["app_emb"]))
     gdp.mode_ = TRAIN
-    o, d, cam = sc.rays(n_rays, seed=1234 + rank)                 # rank-sharded rays (weak scaling)
+    rays = args.rays or cfg["rays"]
+    if cfg["scaling"] == "strong":                                 # one global batch, rank r renders its slice
+        n_draw, seed, lo, hi = rays, 2023, rank * (rays // world), (rank + 1) * (rays // world)
+    else:                                                          # rank-sharded i.i.d. batches (weak scaling)
+        n_draw, seed, lo, hi = rays, 2023 + rank, 0, rays
+    if sb["synthetic"] is not None:
+        o, d, cam = sb["synthetic"].rays(n_draw, seed=1234 + (0 if cfg["scaling"] == "strong" else rank))
+    else:                                                          # the product's own ray generation (N3) on the reference's cameras
+        g = sb["golden"]
+        gen = RayGenerator(g["ds_poses"].reshape(-1, 3, 4), g["ds_intri"].reshape(-1, 3, 3), g["ds_dist_params"], g["ds_bounds"],
+                           images=None, height=int(g["ds_hw"][0]), width=int(g["ds_hw"][1]), train_set=g["ds_train_set"].tolist(),
+                           device=device)
+        torch.manual_seed(seed)
+        (ro, rd, _), _, cam_d = gen.RandRaysData(n_draw)
+        o, d, cam = ro.cpu().numpy(), rd.cpu().numpy(), cam_d.cpu().numpy()
+        prob_gen = gen
+    o, d, cam = (np.ascontiguousarray(x[lo:hi]) for x in (o, d, cam))
     rng = np.random.default_rng(99 + rank)
-    gt = rng.random((n_rays, 3), dtype=np.float32)
-    return dict(scene=sc, gdp=gdp, sampler=sampler, field=field, shader=shader, renderer=renderer,
-                host=(o, d, cam, gt), blobs=(nodes, trans, edges))
+    gt = rng.random((hi - lo, 3), dtype=np.float32)
+    return dict(gdp=gdp, sampler=sampler, field=field, shader=shader, renderer=renderer, cfg=cfg, n_rays=hi - lo,
+                host=(o, d, cam, gt), blobs=(nodes, trans, edges), n_images=sb["n_images"],
+                ray_gen=None if sb["synthetic"] is not None else prob_gen)
 
 
 def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None):
@@ -175,7 +214,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
         from f2nerf_b200.dist import allreduce_step
         dist_sync = allreduce_step
-    prob = build_problem(rank, args.rays, args.log2_table, device)
+    prob = build_problem(rank, world, args, device)
+    n_rays = prob["n_rays"]                                     # rays THIS rank renders per step
     if world > 1:
         from f2nerf_b200.dist import install_vote_sync
         install_vote_sync(prob["sampler"])
@@ -282,19 +322,16 @@ def run_ours(args):
         roof = dict(bound="hbm", achieved=byts / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(name), kernel=name, ms_per_launch=per_launch_ms,
                 share_of_step=rec["ms"] / max(total_traced, 1e-9), peak_source=peaks["src"])
-    rays_total = args.rays * world * args.steps
+    rays_total = n_rays * world * args.steps
+    cfg = prob["cfg"]
     line = {
         "metric": "training rays/sec", "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 march/composite, f16 hash table + MLP operands (f32 accumulate)",
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32 march/composite, f16 hash table + MLP operands (f32 accumulate)",
         "data": "synthetic", "samples_per_sec": n_samples / (ms * 1e-3),
-        "config": {"workload": "ngp_fox-shaped batch (BASELINE configs[1]): 4096 rays x <=1024 samples per GPU, "
-                               "wanjinyou.yaml sampler (near 0.01, scale_by_dis, sample_l 1/256, fineness 1), log2_table_size "
-                               f"{args.log2_table}, synthetic 24-camera scene, random-init table/MLPs, Render+loss+backward",
-                   "rays_per_gpu": args.rays, "samples_per_ray": n_samples / args.steps / world / args.rays,
-                   "kept_per_ray": n_kept / args.steps / world / args.rays, "parallelism": f"dp{world} (rays sharded, params replicated)",
-                   "l2": "per-step working set (>=184 MB of samples + 64 MB table) exceeds the 126 MB L2; no explicit flush",
-                   "mlp_impl": int(_lib.lib.f2b_get_mlp_impl())},
+        "config": config_dict(args, world),
+        "workload_measured": {"samples_per_ray": n_samples / args.steps / world / n_rays, "kept_per_ray": n_kept / args.steps / world / n_rays,
+                              "mlp_impl": int(_lib.lib.f2b_get_mlp_impl())},
         "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in (h_o, h_d, h_cam, h_gt))) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
@@ -307,11 +344,12 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port(prob, args, budget_s=20.0)
+            line["cpu_baseline"] = cpu_port(args, budget_s=20.0)
         if world == 1:
             line["optimizer_step"] = optimizer_timing(prob)
             line["forward_only"] = forward_only_timing(prob, d_o, d_d, args)
-            line["ray_generation"] = ray_generation_timing(prob, args)
+            if prob["ray_gen"] is not None:
+                line["ray_generation"] = ray_generation_timing(prob, args)
         ref_gpu = reference_gpu_timing(args)
         if ref_gpu is not None:
             line["reference_gpu"] = ref_gpu
@@ -341,7 +379,7 @@ def forward_only_timing(prob, d_o, d_d, args, iters=20):
     finally:
         gdp.mode_ = TRAIN
     ms = e0.elapsed_time(e1) / iters
-    return {"value": args.rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
+    return {"value": prob["n_rays"] / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
             "note": "the reference's number is reference_gpu.ms_validate_median on the same ray count"}
 
 
@@ -352,29 +390,24 @@ def ray_generation_timing(prob, args, iters=20):
     a CPU image tensor, three H2D copies, ray kernel.  ngp_fox geometry: 50 images of 960 x 540."""
     import torch
     from f2nerf_b200 import RayGenerator
-    sc = prob["scene"]
-    n_img, H, W = 50, 960, 540
+    src = prob["ray_gen"]                                        # the reference's ngp_fox cameras (fixture)
+    n_img, H, Wd = src.n_images_, src.height_, src.width_
     g = torch.Generator().manual_seed(0)
-    images = torch.rand((n_img, H, W, 3), generator=g)
-    c2w = np.asarray(sc.c2w, np.float32)
-    poses = np.tile(c2w[:1, :3, :4], (n_img, 1, 1)).astype(np.float32)
-    poses[:len(c2w)] = c2w[:n_img, :3, :4]
-    intri = np.tile(np.array([[687.6, 0, 270.], [0, 687.2, 480.], [0, 0, 1]], np.float32), (n_img, 1, 1))
-    dist = np.tile(np.array([0.057, -0.0787, -0.0019, -0.0025], np.float32), (n_img, 1))
-    bounds = np.tile(np.array([0.1, 10.], np.float32), (n_img, 1))
-    gen = RayGenerator(poses, intri, dist, bounds, images=images)
+    images = torch.rand((n_img, H, Wd, 3), generator=g)
+    gen = RayGenerator(src.poses_, src.intri_, src.dist_params_, src.bounds_, images=images, train_set=src.train_set_)
+    n_b = prob["n_rays"]
     dev = gen.poses_.device
     flat = images.view(-1, 3)
 
     def ours():
-        gen.RandRaysData(args.rays)
+        gen.RandRaysData(n_b)
 
     def ref_style():
-        cam = torch.randint(n_img, (args.rays,), dtype=torch.int64)
-        i = torch.randint(0, H, (args.rays,), dtype=torch.int64)
-        j = torch.randint(0, W, (args.rays,), dtype=torch.int64)
+        cam = torch.randint(n_img, (n_b,), dtype=torch.int64)
+        i = torch.randint(0, H, (n_b,), dtype=torch.int64)
+        j = torch.randint(0, Wd, (n_b,), dtype=torch.int64)
         ij = torch.stack([i, j], -1).to(dev).contiguous()
-        gt = flat[cam * H * W + i * W + j].to(dev).contiguous()
+        gt = flat[cam * H * Wd + i * Wd + j].to(dev).contiguous()
         cam_d = cam.to(dev)
         gen.Img2WorldRayFlex(cam_d.to(torch.int32), ij.to(torch.int32))
         return gt, gen.bounds_[cam_d].contiguous()
@@ -433,106 +466,115 @@ def optimizer_timing(prob, iters=20):
 
 
 def reference_gpu_timing(args):
-    """Informational: the compiled, unmodified reference (oracle/_ref/ref_driver) timed on the same box."""
+    """Informational, N=1 only: the compiled, unmodified reference (oracle/_ref/ref_driver, built by build() from
+    /root/reference) timed on the same box, same config YAML, same ngp_fox scene, same seeded ray batch (seed 2023) and
+    parameter state as the product arm.  CUDA events around its own Renderer::Render + loss.backward(), median of 20."""
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    if args.no_ref_gpu or not os.path.exists(drv) or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    cfg = W.CONFIGS[args.config]
+    if args.no_ref_gpu or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return None
+    if cfg["ref_yaml"] is None:
+        return {"unavailable": "synthetic scene: the reference builds its octree from a dataset"}
+    if not os.path.exists(drv):
+        return {"unavailable": "oracle/_ref/ref_driver not built (build() makes it when /root/reference is present)"}
     try:
         out_dir = "/tmp/f2b_ref_bench"
-        subprocess.run([drv, os.path.join(ROOT, "oracle", "ref_config_ngp_fox.yaml"), out_dir, str(args.rays), "20"],
-                       cwd=ROOT, capture_output=True, text=True, timeout=600)
-        return json.load(open(os.path.join(out_dir, "ref_timing.json")))
+        r = subprocess.run([drv, os.path.join(ROOT, cfg["ref_yaml"]), out_dir, str(args.rays or cfg["rays"]), "20"],
+                           cwd=ROOT, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return {"unavailable": ("ref_driver rc %d: " % r.returncode) + r.stderr[-160:]}
+        t = json.load(open(os.path.join(out_dir, "ref_timing.json")))
+        t["config_yaml"] = cfg["ref_yaml"]
+        t["note"] = "unmodified Totoro97/f2-nerf + tiny-cuda-nn compiled for sm_100a; same scene / rays / parameters as the product arm"
+        return t
     except Exception as e:  # noqa: BLE001
         return {"unavailable": str(e)[:200]}
 
 
-def cpu_port(prob, args, budget_s=20.0):
-    """The CPU restatement (oracle) of the same step on a bounded sample of the same workload."""
-    import oracle_lib as O
-    import oracle_pipeline as OP
-    import torch
-    nodes, trans, edges = prob["blobs"]
-    o, d, cam, gt = prob["host"]
-    field, shader, renderer = prob["field"], prob["shader"], prob["renderer"]
-    sc = dict(nodes=nodes, trans=trans, edges=edges, near=NEAR, sample_l=SAMPLE_L, scale_by_dis=SCALE_BY_DIS, max_hits=1024)
-    fld = dict(table16=field.feat_pool_.detach().cpu().numpy().astype(np.float16), prim=field.prim_pool_.cpu().numpy(),
-               bias=field.bias_pool_.cpu().numpy(), V=field.n_volumes_, local_size=field.local_size_,
-               mlp_params=field.mlp_.params_.detach().cpu().numpy())
-    sp = shader.mlp_.params_.detach().cpu().numpy()
-    emb = renderer.app_emb_.detach().cpu().numpy()
-    n = 32
-    rng = np.random.default_rng(0)
-    n_edges = edges.size // 64
+class CpuPort:
+    """The CPU restatement (oracle/) of the same step on the same config: same octree blobs, same parameter state, the
+    same seeded ray batch (rays through the oracle's restatement of Img2WorldRayKernel).  Loads no product code."""
 
-    def one(n):
-        dn = (torch.from_numpy(d[:n]) / torch.linalg.norm(torch.from_numpy(d[:n]), 2, -1, True)).numpy()
+    def __init__(self, args):
+        import oracle_lib as O
+        self.O, self.args = O, args
+        cfg = self.cfg = W.CONFIGS[args.config]
+        sb = W.scene_blobs(args.config)
+        V = sb["trans"].size // 544
+        par = W.init_params(args.config, V, sb["n_images"], sb["prim"], sb["bias"])
+        self.sc = dict(nodes=sb["nodes"], trans=sb["trans"], edges=sb["edges"], near=cfg["near"], sample_l=cfg["sample_l"],
+                       scale_by_dis=cfg["scale_by_dis"], max_hits=1024)
+        local = (((1 << cfg["log2_table"]) * 16 // 16) >> 4) << 4
+        self.fld = dict(table16=par["table"].astype(np.float16), prim=par["prim"], bias=par["bias"], V=V, local_size=local,
+                        mlp_params=par["field_mlp"])
+        self.sp, self.emb = par["shader_mlp"], (par["app_emb"] if cfg["use_app_emb"] else None)
+        self.rays = args.rays or cfg["rays"]
+        o, d, cam = W.host_rays(args.config, self.rays, 2023 if sb["synthetic"] is None else 1234)
+        self.o, self.cam = o, cam
+        self.dn = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+        self.rng = np.random.default_rng(0)
+        self.gt = self.rng.random((self.rays, 3), dtype=np.float32)
+        self.n_edges = sb["edges"].size // 64
+
+    def step(self, n):
+        import oracle_pipeline as OP
+        rng = self.rng
         noise = (rng.random(1024 + n + 10, dtype=np.float32) + .5).astype(np.float32)
         bg = rng.random((n, 3), dtype=np.float32)
-        edge = (rng.integers(0, n_edges, 8192).astype(np.int32), (rng.random((8192, 2), dtype=np.float32) * 2 - 1))
+        edge = (rng.integers(0, self.n_edges, 8192).astype(np.int32), (rng.random((8192, 2), dtype=np.float32) * 2 - 1))
         t0 = time.time()
-        OP.render_train(sc, o[:n], dn, noise, bg, fld, sp, emb, cam[:n], edge, gt[:n])
+        OP.render_train(self.sc, self.o[:n], self.dn[:n], noise, bg, self.fld, self.sp, self.emb,
+                        self.cam[:n] if self.emb is not None else None, edge, self.gt[:n])
         return time.time() - t0
-    t = one(n)
-    while t < budget_s / 4 and n < args.rays:
-        n = min(n * 2, args.rays)
-        t = one(n)
+
+    def size_for(self, budget_s, n0=32):
+        """largest power-of-two ray count (<= the batch) whose step fits ``budget_s``; returns (n, seconds of the probe)."""
+        n, t = n0, self.step(n0)
+        while t < budget_s / 2 and n < self.rays:
+            n = min(n * 2, self.rays)
+            t = self.step(n)
+        return n, t
+
+
+def cpu_port(args, budget_s=20.0):
+    import oracle_lib as O
+    port = CpuPort(args)
+    n, t = port.size_for(budget_s / 2)
     return {"value": n / t, "unit": "rays/s", "cores": O.num_threads(), "kind": "port",
-            "sample": f"{n} of the {args.rays} rays of the same batch (all stages incl. backward), {t:.1f} s wall; "
+            "sample": f"{n} of the {port.rays} rays of the same batch (all stages incl. backward), {t:.1f} s wall; "
                       "all stages OpenMP-parallel (oracle/f2_oracle.c)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference has no CPU path and cannot be pip-installed (C++/CUDA executable);
-    this arm times the CPU port of its algorithm (oracle/) with all host threads on a bounded sample."""
+    """--impl reference: the reference has no CPU path (src/Common.h:9-13 hard-codes CUDA tensors; tiny-cuda-nn is CUDA-only)
+    and is a C++/CUDA executable, not a pip package: this arm times the CPU port of its algorithm (oracle/) with all host
+    threads on the product arm's config; every step is a bounded sample (the first n rays of the same seeded batch), n chosen
+    so that the K + W steps end within ~2 minutes.  Imports nothing from the product package."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if "F2B_REF_THREADS" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
         # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host thread it can
         os.environ["OMP_NUM_THREADS"] = os.environ.get("F2B_REF_THREADS", str(os.cpu_count()))
-    import torch  # noqa: F401
-    # the CPU arm needs the same parameters; build them on the CPU without touching the GPU library
     import oracle_lib as O
-    import oracle_pipeline as OP
-    from f2nerf_b200.scene import SyntheticScene
-    sc0 = SyntheticScene(n_cams=24, seed=0)
-    nodes, trans, edges = sc0.blobs()
-    V = trans.size // 544
-    rng = np.random.default_rng(2022)
-    pool = (1 << args.log2_table) * 16
-    fld = dict(table16=(rng.random((pool, 2), dtype=np.float32) * 0.02 - 0.01).astype(np.float16),
-               prim=(rng.integers(1 << 28, 1 << 30, size=(16, V, 3)).astype(np.int32) | 1),
-               bias=(rng.random((16 * V, 3), dtype=np.float32) * 1000 + 100), V=V, local_size=1 << args.log2_table,
-               mlp_params=O.mlp_init(32, 0))
-    sp = O.mlp_init(32, 1)
-    emb = (rng.standard_normal((24, 16)) * .1).astype(np.float32)
-    sc = dict(nodes=nodes, trans=trans, edges=edges, near=NEAR, sample_l=SAMPLE_L, scale_by_dis=SCALE_BY_DIS, max_hits=1024)
-    o, d, cam = sc0.rays(args.rays, seed=1234)
-    gt = rng.random((args.rays, 3), dtype=np.float32)
-    n = min(args.rays, args.ref_rays)
-    dn = (d[:n] / np.linalg.norm(d[:n], axis=-1, keepdims=True)).astype(np.float32)
-    n_edges = edges.size // 64
-
-    def step():
-        noise = (rng.random(1024 + n + 10, dtype=np.float32) + .5).astype(np.float32)
-        bg = rng.random((n, 3), dtype=np.float32)
-        edge = (rng.integers(0, n_edges, 8192).astype(np.int32), (rng.random((8192, 2), dtype=np.float32) * 2 - 1))
-        OP.render_train(sc, o[:n], dn, noise, bg, fld, sp, emb, cam[:n], edge, gt[:n])
-    for _ in range(min(args.warmup, 1)):
-        step()
+    port = CpuPort(args)
+    n, _ = port.size_for(120.0 / max(args.steps + args.warmup, 1)) if not args.ref_rays else (min(args.ref_rays, port.rays), 0)
+    for _ in range(args.warmup):
+        port.step(n)
     t0 = time.time()
     for _ in range(args.steps):
-        step()
+        port.step(n)
     dt = time.time() - t0
     v = n * args.steps / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     print(json.dumps({
         "impl": "reference", "metric": "training rays/sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (CPU port)", "data": "synthetic",
-        "config": {"workload": f"same batch shape as the product arm; each step = {n} of the {args.rays} rays (bounded sample)",
-                   "rays_per_step": n},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": W.CONFIGS[args.config]["scaling"], "vs_baseline": None, "dtype": "f32 (CPU port, fp16 table / MLP operands)",
+        "data": "synthetic", "config": config_dict(args, world),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": O.num_threads(), "kind": "port",
-                         "sample": f"{n} rays x <=1024 samples per step, all stages incl. backward"},
+                         "sample": f"each step = the first {n} of the {port.rays} rays of the product arm's seeded batch x <=1024 samples, "
+                                   "all stages incl. backward"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -542,9 +584,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=N_RAYS)
-    ap.add_argument("--log2-table", dest="log2_table", type=int, default=LOG2_TABLE)
-    ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=256)
+    ap.add_argument("--config", default="wanjinyou", choices=sorted(W.CONFIGS))
+    ap.add_argument("--rays", type=int, default=0, help="override the config's ray count (global for strong-scaling configs)")
+    ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=0, help="--impl reference: rays per step (0 = sized to ~2 min total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()

@@ -6,8 +6,10 @@
 
 namespace f2b {
 
-// degree-4 real spherical harmonics in tiny-cuda-nn ordering (SHShader.cu:32-50); every product / sum rounded
-// separately (no contraction), so the stand-alone operator and the fused epilogue agree bit for bit
+// degree-4 real spherical harmonics in tiny-cuda-nn ordering (SHShader.cu:32-50).  Explicit roundings, in the
+// contraction pattern ptxas chose for the reference TU (-fmad=true; read off the SASS of the reference build):
+// o6 = fma(c,z2,-k), o8 = fma(c,x2,-(c*y2)), the inner factors of o9/o11/o12/o13/o15 are single FMAs.  Both users
+// (stand-alone operator, fused epilogue) spell out the same sequence => rows bit-identical to the reference kernel's.
 __device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
   const float xy = fmul(x, y), xz = fmul(x, z), yz = fmul(y, z), x2 = fmul(x, x), y2 = fmul(y, y), z2 = fmul(z, z);
   o[0] = 0.28209479177387814f;
@@ -16,16 +18,17 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float o[16]) {
   o[3] = fmul(-0.48860251190291987f, x);
   o[4] = fmul(1.0925484305920792f, xy);
   o[5] = fmul(-1.0925484305920792f, yz);
-  o[6] = fsub(fmul(0.94617469575755997f, z2), 0.31539156525251999f);
+  o[6] = __fmaf_rn(z2, 0.94617469575755997f, -0.31539156525251999f);
   o[7] = fmul(-1.0925484305920792f, xz);
-  o[8] = fsub(fmul(0.54627421529603959f, x2), fmul(0.54627421529603959f, y2));
-  o[9] = fmul(fmul(0.59004358992664352f, y), fadd(fmul(-3.0f, x2), y2));
-  o[10] = fmul(fmul(2.8906114426405538f, xy), z);
-  o[11] = fmul(fmul(0.45704579946446572f, y), fsub(1.0f, fmul(5.0f, z2)));
-  o[12] = fmul(fmul(0.3731763325901154f, z), fsub(fmul(5.0f, z2), 3.0f));
-  o[13] = fmul(fmul(0.45704579946446572f, x), fsub(1.0f, fmul(5.0f, z2)));
-  o[14] = fmul(fmul(1.4453057213202769f, z), fsub(x2, y2));
-  o[15] = fmul(fmul(0.59004358992664352f, x), fadd(-x2, fmul(3.0f, y2)));
+  o[8] = __fmaf_rn(x2, 0.54627421529603959f, -fmul(y2, 0.54627421529603959f));
+  o[9] = fmul(fmul(y, 0.59004358992664352f), __fmaf_rn(x2, -3.0f, y2));
+  o[10] = fmul(z, fmul(xy, 2.8906114426405538f));
+  const float f15 = __fmaf_rn(z2, -5.0f, 1.0f);
+  o[11] = fmul(fmul(y, 0.45704579946446572f), f15);
+  o[12] = fmul(fmul(z, 0.3731763325901154f), __fmaf_rn(z2, 5.0f, -3.0f));
+  o[13] = fmul(f15, fmul(x, 0.45704579946446572f));
+  o[14] = fmul(fmul(z, 1.4453057213202769f), fsub(x2, y2));
+  o[15] = fmul(fmul(x, 0.59004358992664352f), __fmaf_rn(y2, 3.0f, -x2));
 }
 
 // Shader-MLP input row: fp16([1, feat[1..15]] + app_emb[cam] | SH4(dir)) (Renderer.cpp:179-187, SHShader.cpp:23-26,

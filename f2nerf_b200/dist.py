@@ -30,28 +30,33 @@ def install_vote_sync(sampler):
 
 
 def allreduce_grads(renderer):
-    """The post-backward exchange step; returns the number of bytes each rank contributed."""
+    """The post-backward exchange step; returns the number of bytes each rank contributed.  Every rank issues the SAME
+    fixed-shape collectives whether or not its own batch produced gradients (a rank whose rays all missed the octree
+    contributes zeros), so ranks can never disagree on the collective sequence."""
     world = dist.get_world_size()
     field, shader = renderer.scene_field_, renderer.shader_
-    small = [p for p in (field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_) if p.grad is not None]
+    params = (field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_)
     sent = 0
-    if field.feat_pool_.grad is not None:
-        g = field.feat_pool_.grad[:live_rows(field)]
-        dist.all_reduce(g)
-        g.div_(world)
-        sent += g.numel() * g.element_size()
-    if small:
-        flat = torch.cat([p.grad.reshape(-1) for p in small])
-        flag = getattr(renderer, "nonfinite_flag_", None)
-        flat = torch.cat([flat, (flag if flag is not None else torch.zeros((), dtype=torch.bool, device=flat.device)).float().reshape(1) * world])
-        dist.all_reduce(flat)
-        flat.div_(world)
-        off = 0
-        for p in small:
-            n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad)); off += n
-        renderer.nonfinite_flag_ = flat[off] > 0            # OR across ranks
-        sent += flat.numel() * 4
+    if field.feat_pool_.grad is None:
+        field.feat_pool_.grad = torch.zeros_like(field.feat_pool_)
+    g = field.feat_pool_.grad[:live_rows(field)]
+    dist.all_reduce(g)
+    g.div_(world)
+    sent += g.numel() * g.element_size()
+    dev = field.feat_pool_.device
+    flag = getattr(renderer, "nonfinite_flag_", None)
+    flag = torch.zeros(2, device=dev) if flag is None else flag.reshape(-1).float().expand(2) if flag.numel() == 1 else flag.float()
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] + [flag * world])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            p.grad = torch.empty_like(p)
+        p.grad.copy_(flat[off:off + n].view_as(p)); off += n
+    renderer.nonfinite_flag_ = flat[off:off + 2] > 0        # OR across ranks, per MLP
+    sent += flat.numel() * 4
     return sent
 
 

@@ -133,10 +133,11 @@ class Hash3DAnchored:
         self.feat_pool_.requires_grad_(True)
         n = 3 * N_LEVELS * self.n_volumes_
         if prim_pool is None:
-            prims = []                      # rejection-sampled primes in [2^28, 2^30) (Hash3DAnchored.cpp:46-57)
-            while len(prims) < n:
-                cand = torch.randint(1 << 28, 1 << 30, (max(4 * (n - len(prims)), 64),), dtype=torch.int64).tolist()
-                prims.extend(v for v in cand if _is_prime(v))
+            prims = []                      # rejection-sampled primes in [2^28, 2^30): ONE int32 draw per trial on the CPU
+            while len(prims) < n:           # generator, as Hash3DAnchored.cpp:49-55 does, so the generator is left in the same
+                v = int(torch.randint(1 << 28, 1 << 30, (1,), dtype=torch.int32).item())   # state for the draws that follow
+                if _is_prime(v):
+                    prims.append(v)
             prim_pool = torch.tensor(prims[:n], dtype=torch.int32)
         self.prim_pool_ = torch.as_tensor(prim_pool, dtype=torch.int32).reshape(N_LEVELS, self.n_volumes_, 3).to(dev).contiguous()
         if bias_pool is None:

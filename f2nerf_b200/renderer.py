@@ -351,20 +351,38 @@ class _RenderFunction(torch.autograd.Function):
         main.wait_stream(side)
         d_sparams = d_sparams / s_scale
         d_fparams = d_fparams / f_scale
-        # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240); one fused finiteness test
-        bad = ~(torch.isfinite(d_sparams).all() & torch.isfinite(d_fparams).all())
-        renderer.nonfinite_flag_ = bad
+        # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240): the reference tests dL/dparams AND dL/dinput of
+        # each MLP.  The shader MLP's input gradient reaches d_app (and the field MLP's dL/dout), the field MLP's input
+        # gradient reaches every table-gradient entry its samples touch, so those stand in for the fp16 tensors
+        # themselves (a non-finite fp16 element cannot disappear on the way: w * inf / NaN stays non-finite).
+        live = min(d_table.shape[0], (17 * int(field.local_size_)) // 2)
+        ok_s = torch.isfinite(d_sparams).all()
+        if d_app is not None:
+            ok_s = ok_s & torch.isfinite(d_app).all()
+        ok_f = torch.isfinite(d_fparams).all() & torch.isfinite(d_table[:live]).all()
+        bad = torch.stack([~ok_s, ~ok_f])                          # [shader, field], device-side, no sync here
+        prev = getattr(renderer, "nonfinite_flag_", None)
+        renderer.nonfinite_flag_ = bad if prev is None else (prev | bad)      # OR: a second backward must not erase a hit
         ctx.pack = None                               # saved activations (~1 GB at 4 M samples) die with the backward, not with `res`
         return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None, None
 
 
 def check_backward_nan(renderer):
-    """Host read of the device-side NaN flag set by the last backward (one sync); applies the reference's
-    loss-scale halving and sets ``global_data_pool_.backward_nan_`` (ExpRunner.cpp:131-134 reads it)."""
+    """Host read of the device-side NaN flags accumulated by the backward passes since the last call (one sync);
+    applies the reference's loss-scale halving to the MLP(s) that produced the non-finite values and sets
+    ``global_data_pool_.backward_nan_`` — the flag ExpRunner.cpp:131-134 reads right after ``loss.backward()``.
+    A trainer MUST call this between ``backward()`` and ``optimizer.step()`` (FusedAdam.step(renderer=...) does)."""
     flag = getattr(renderer, "nonfinite_flag_", None)
-    if flag is not None and bool(flag.item()):
-        renderer.global_data_pool_.backward_nan_ = True
-        for m in (renderer.scene_field_.mlp_, renderer.shader_.mlp_):
+    renderer.nonfinite_flag_ = None
+    if flag is None:
+        return False
+    hit = flag.reshape(-1).tolist()
+    if len(hit) == 1:
+        hit = [hit[0], hit[0]]
+    for m, h in ((renderer.shader_.mlp_, hit[0]), (renderer.scene_field_.mlp_, hit[1])):
+        if h:
             m.loss_scale_ = max(m.loss_scale_ / 2.0, 1.0)
+    if any(hit):
+        renderer.global_data_pool_.backward_nan_ = True
         return True
     return False

@@ -6,7 +6,7 @@ Same method names and argument meaning as the reference class (``GetSamples``, `
 reference's ``CUDAFloat`` / ``CUDAInt``.  RNG draws use the same torch calls in the same order as the
 reference so that a shared ``torch.manual_seed`` reproduces its noise (``PersSampler.cu:377,456-457``).
 Octree (re)construction / compaction (``PersOctree::ProcOctree``) is out of scope (SURVEY §8f N2):
-blobs come from a reference checkpoint / dump or from :mod:`f2nerf_b200.scene`.
+blobs come from a reference checkpoint / dump or from ``tests/synth_scene.py`` (synthetic scenes for tests and the bench).
 """
 from dataclasses import dataclass
 

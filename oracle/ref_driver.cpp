@@ -9,6 +9,8 @@
 // The dumps pin oracle/f2_oracle.c and the CUDA kernels (tests/golden/, tests/test_ref_parity.py).
 //
 //   ref_driver <runtime_config.yaml> <out_dir> <n_rays> [n_time_iters=0] [dump_full_grads=0]
+//   ref_driver --train <runtime_config.yaml>      what the reference's main.cpp does: ExpRunner(conf).Execute() — the
+//                                                 unmodified trainer (train to end_iter, then TestImages -> mean PSNR)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -19,7 +21,9 @@
 #include <cuda_runtime.h>
 #ifdef F2B_WITH_SHIM
 #include "../f2nerf_b200/shim/B200Ops.h"
+#include "../f2nerf_b200/shim/B200Renderer.h"
 #endif
+#include "ExpRunner.h"
 #include "Common.h"
 #include "Utils/GlobalDataPool.h"
 #include "Utils/cnpy.h"
@@ -53,6 +57,12 @@ static void dump(const std::string& name, const Tensor& t_in) {
 static void dump_scalar(const std::string& name, float v) { dump(name, torch::full({1}, v, CPUFloat)); }
 
 int main(int argc, char** argv) {
+  if (argc >= 3 && std::string(argv[1]) == "--train") {     // main.cpp:6-13 verbatim in behaviour
+    torch::manual_seed(2022);
+    auto exp_runner = std::make_unique<ExpRunner>(argv[2]);
+    exp_runner->Execute();
+    return 0;
+  }
   if (argc < 4) { std::fprintf(stderr, "usage: ref_driver <config.yaml> <out_dir> <n_rays> [n_time_iters] [dump_full_grads]\n"); return 1; }
   const std::string conf_path = argv[1];
   g_out = argv[2];
@@ -83,10 +93,15 @@ int main(int argc, char** argv) {
   }
 
 #ifdef F2B_WITH_SHIM
-  // ---- ref_driver_b200 only: the operator-level drop-in.  The reference's OWN Renderer::Render / autograd / loss now drive
-  // the B200 subclasses: same octree object, same parameters, so every dump below is directly comparable
-  // with the pure-reference run of oracle/_ref/ref_driver.  Never built into ref_driver (the reference arm stays unmodified).
-  {
+  // ---- ref_driver_b200 only.  Default (F2B_SHIM unset or "fused"): the body of Renderer::Render is the fused B200 host
+  // (f2nerf_b200/shim/B200Renderer.cpp) working on the reference's own operator objects.  F2B_SHIM=ops: the operator-level
+  // drop-in — the reference's OWN Renderer::Render / autograd / loss drive the B200 subclasses: same octree
+  // object, same parameters.  Either way every dump below is directly comparable with the pure-reference run of
+  // oracle/_ref/ref_driver.  Never built into ref_driver (the reference arm stays unmodified).
+  const char* shim_env = std::getenv("F2B_SHIM");
+  const bool shim_ops = shim_env && std::string(shim_env) == "ops";
+  if (shim_ops) {
+    f2b_render_use_reference(true);
     auto b_sampler = std::make_unique<B200Sampler>(gdp.get());
     b_sampler->pers_octree_ = std::move(sampler->pers_octree_);          // the very same octree / warps / edge pool
     auto b_field = std::make_unique<B200HashField>(gdp.get());
@@ -101,6 +116,9 @@ int main(int argc, char** argv) {
     shader = dynamic_cast<SHShader*>(renderer->shader_.get());
     CHECK(sampler && field && shader);
     std::printf("ref_driver_b200: PersSampler / Hash3DAnchored / SHShader replaced by the B200 subclasses\n");
+  } else {
+    f2b_render_keep_samples(true);                                       // the dumps read renderer->sample_result_
+    std::printf("ref_driver_b200: Renderer::Render replaced by the fused B200 host\n");
   }
 #endif
 
@@ -170,6 +188,7 @@ int main(int argc, char** argv) {
     dump("val_scene_feat", feat);
     Tensor shading = torch::cat({torch::ones_like(feat.index({Slc(), Slc(0, 1)})), feat.index({Slc(), Slc(1, None)})}, 1);
     dump("val_rgb", shader->Query(shading, s.dirs));
+    dump("val_sh", shader->SHEncode(s.dirs));
     auto r = renderer->Render(rays_o, rays_d, bounds, Tensor());
     dump("val_colors", r.colors); dump("val_disparity", r.disparity); dump("val_depth", r.depth);
     dump("val_weights", r.weights); dump("val_idx_start_end", r.idx_start_end);
@@ -237,6 +256,9 @@ int main(int argc, char** argv) {
 
   // ---- timing: Render + backward, CUDA events on the default stream ------------------------------
   if (n_time > 0) {
+#ifdef F2B_WITH_SHIM
+    f2b_render_keep_samples(false);
+#endif
     std::vector<float> ms_fwd, ms_all;
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);

@@ -23,7 +23,7 @@ def oracle():
 @pytest.fixture(scope="session")
 def scene():
     """Small synthetic scene (833 nodes / 184 warps): octree + warp + edge blobs as numpy u8."""
-    from f2nerf_b200.scene import SyntheticScene
+    from synth_scene import SyntheticScene
     sc = SyntheticScene(n_cams=24, seed=0)
     nodes, trans, edges = sc.blobs()
     return dict(scene=sc, nodes=nodes, trans=trans, edges=edges, n_volumes=trans.size // 544)

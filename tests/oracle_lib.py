@@ -232,3 +232,12 @@ def octree_proc(nodes, wstat, astat, visit, subdivide, brute_force=False):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def mark_invisible(nodes, intri, w2c, bound):
+    """PersOctree::MarkInvisibleNodes restated (oracle/f2_oracle.c: orc_mark_invisible) -> nodes bytes with trans_idx = -1
+    on every node no camera sees."""
+    out = c(nodes, np.uint8).copy()
+    intri, w2c, bound = c(intri, np.float32), c(w2c, np.float32), c(bound, np.float32)
+    lib().orc_mark_invisible(_p(out), I(out.size // 64), _p(intri), _p(w2c), _p(bound), I(bound.size // 2))
+    return out

@@ -24,7 +24,7 @@ def _worker(rank, world, port, q):
                             mlp_=SimpleNamespace(params_=torch.zeros(3072, requires_grad=True)))
     shader = SimpleNamespace(mlp_=SimpleNamespace(params_=torch.zeros(7168, requires_grad=True)))
     renderer = SimpleNamespace(scene_field_=field, shader_=shader, app_emb_=torch.zeros(5, 16, requires_grad=True),
-                               nonfinite_flag_=torch.tensor(rank == 1))
+                               nonfinite_flag_=torch.tensor([rank == 1, False]))
     g = torch.Generator().manual_seed(rank)
     live = fd.live_rows(field)
     assert live == 17 * local // 2
@@ -32,8 +32,9 @@ def _worker(rank, world, port, q):
     field.feat_pool_.grad[:live] = torch.rand(live, 2, generator=g)
     field.mlp_.params_.grad = torch.rand(3072, generator=g)
     shader.mlp_.params_.grad = torch.rand(7168, generator=g)
-    renderer.app_emb_.grad = torch.rand(5, 16, generator=g)
-    mine = [field.feat_pool_.grad.clone(), field.mlp_.params_.grad.clone(), shader.mlp_.params_.grad.clone(), renderer.app_emb_.grad.clone()]
+    renderer.app_emb_.grad = torch.rand(5, 16, generator=g) if rank == 0 else None   # a rank with no gradient (empty batch)
+    zero_if_none = lambda t, like: torch.zeros_like(like) if t is None else t.clone()
+    mine = [field.feat_pool_.grad.clone(), field.mlp_.params_.grad.clone(), shader.mlp_.params_.grad.clone(), zero_if_none(renderer.app_emb_.grad, renderer.app_emb_)]
     sent = fd.allreduce_grads(renderer)
     got = [field.feat_pool_.grad, field.mlp_.params_.grad, shader.mlp_.params_.grad, renderer.app_emb_.grad]
     # octree votes: MAX across ranks
@@ -47,7 +48,7 @@ def _worker(rank, world, port, q):
     gdp = GlobalDataPool()
     gdp.sampled_pts_per_ray_ = 100.0 + 50 * rank
     fd.sync_emas(gdp)
-    q.put((rank, [t.numpy() for t in mine], [t.numpy() for t in got], bool(renderer.nonfinite_flag_), sent,
+    q.put((rank, [t.numpy() for t in mine], [t.numpy() for t in got], renderer.nonfinite_flag_.tolist(), sent,
            vw.tolist(), va.tolist(), mk.tolist(), vc.tolist(), gdp.sampled_pts_per_ray_))
     dist.destroy_process_group()
 
@@ -67,8 +68,8 @@ def test_allreduce_step_world2():
     for a, b, ga, gb in zip(m0, m1, g0, g1):
         np.testing.assert_allclose(ga, (a + b) / 2, rtol=1e-6)           # averaged gradient, identical on both ranks
         np.testing.assert_array_equal(ga, gb)
-    assert f0 and f1                                                    # NaN flag is OR-ed
-    assert s0 == s1 == (17 * 256 // 2) * 2 * 4 + (3072 + 7168 + 80 + 1) * 4   # only the live prefix of the table travels
+    assert f0 == f1 == [True, False]                                    # NaN flags are OR-ed per MLP; same collectives on both ranks
+    assert s0 == s1 == (17 * 256 // 2) * 2 * 4 + (3072 + 7168 + 80 + 2) * 4   # only the live prefix of the table travels
     assert v0[0] == v1[0] == [-1, 512, 512, -1] and v0[1] == v1[1] == [32, -1, -1, -1]
     assert v0[2] == v1[2] == [1, 1, 1, 0] and v0[3] == v1[3] == [3, 9, 4, 0]
     assert abs(v0[4] - 125.0) < 1e-9 and v0[4] == v1[4]

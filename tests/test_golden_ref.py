@@ -150,3 +150,20 @@ def test_octree_maintenance_vs_reference(g, oracle):
     on, ow, oa = oracle.octree_proc(g["oct_nodes_invis"], g["oct_w_sub"], g["oct_a_sub"], visit0, False, False)
     np.testing.assert_array_equal(_node_fields(on), _node_fields(g["oct_nodes_final"]))
     np.testing.assert_array_equal(ow, g["oct_w_final"]); np.testing.assert_array_equal(oa, g["oct_a_final"])
+
+
+def test_mark_invisible_vs_reference(g, oracle):
+    """PersOctree::MarkInvisibleNodes (PersSampler.cu:617-680) on the reference's subdivided ngp_fox octree with its own
+    training cameras: the restatement marks exactly the nodes the reference marked."""
+    out = oracle.mark_invisible(g["oct_nodes_sub"], g["oct_intri"], g["oct_w2c"], g["oct_bound"])
+    mine = out.view(np.int32).reshape(-1, 16)[:, 14]
+    theirs = np.ascontiguousarray(g["oct_nodes_invis"]).view(np.uint8).view(np.int32).reshape(-1, 16)[:, 14]
+    assert (theirs < 0).sum() > (np.ascontiguousarray(g["oct_nodes_sub"]).view(np.uint8).view(np.int32).reshape(-1, 16)[:, 14] < 0).sum()
+    np.testing.assert_array_equal(mine, theirs)
+    np.testing.assert_array_equal(_node_fields(out), _node_fields(g["oct_nodes_invis"]))
+
+
+def test_sh4_bit_exact_vs_reference(g, oracle):
+    """SHKenerl (SHShader.cu:25-50): the reference TU is built -fmad=true; the restatement spells out the contraction
+    ptxas chose (read off the reference build's SASS), so the degree-4 encoding matches bit for bit."""
+    np.testing.assert_array_equal(bits(oracle.sh4(g["val_dirs"])), bits(g["val_sh"]))

@@ -697,3 +697,29 @@ def test_octree_proc_matches_oracle(scene, oracle, frac):
 def make_rays_for(scene, n):
     from conftest import make_rays
     return make_rays(scene, n, seed=3)
+
+
+def test_octree_mark_invisible_matches_oracle(scene, oracle):
+    """f2b_octree_mark_invisible (PersSampler.cu:617-680) == the sequential restatement, byte for byte: cameras that see the
+    scene, cameras that see nothing (looking away / depth window beyond it), and a camera sitting inside a node's sphere."""
+    from f2nerf_b200 import GlobalDataPool, PersSampler
+    sc = scene["scene"]
+    c2w = np.asarray(sc.c2w, np.float32)[:, :3, :4]
+    R, t = c2w[:, :, :3], c2w[:, :, 3]
+    w2c = np.concatenate([R.transpose(0, 2, 1), -(R.transpose(0, 2, 1) @ t[:, :, None])], 2).astype(np.float32)
+    n = w2c.shape[0]
+    intri = np.tile(np.array([[255., 0, 100.], [0, 255., 56.], [0, 0, 1]], np.float32), (n, 1, 1))
+    for keep, bnd in ((slice(0, n), (0.05, 6.0)), (slice(0, 3), (0.05, 0.6)), (slice(0, 2), (50., 60.)), (slice(0, 0), (0.05, 6.0))):
+        bound = np.tile(np.array(bnd, np.float32), (n, 1))[keep]
+        gdp = GlobalDataPool()
+        sampler = PersSampler(gdp, scene["nodes"], scene["trans"], scene["edges"])
+        if bound.shape[0]:
+            sampler.MarkInvisibleNodes(intri[keep], w2c[keep], bound)
+        else:                                                    # no cameras: every node is invisible
+            from f2nerf_b200._lib import call, stream
+            z = torch.zeros(1, device="cuda")
+            call("f2b_octree_mark_invisible", sampler.tree_nodes_gpu_, sampler.n_nodes, z, z, z, 0, stream())
+        want = oracle.mark_invisible(scene["nodes"], intri[keep], w2c[keep], bound)
+        np.testing.assert_array_equal(N(sampler.tree_nodes_gpu_), want.reshape(-1))
+    ti = want.view(np.int32).reshape(-1, 16)[:, 14]
+    assert (ti < 0).all()

@@ -42,7 +42,7 @@ def test_sampler_structure(scene, oracle):
     b = s["bounds"]
     assert (b[:, 0] <= b[:, 1]).all() and b[0, 0] == 0 and (b[1:, 0] == b[:-1, 1]).all()
     assert b[-1, 1] == s["pts"].shape[0] and ((b[:, 1] - b[:, 0]) <= 1024).all()
-    from f2nerf_b200.scene import view_nodes
+    from synth_scene import view_nodes
     nodes = view_nodes(scene["nodes"])
     for r in range(64):
         sl = slice(b[r, 0], b[r, 1])
@@ -58,7 +58,7 @@ def test_sampler_structure(scene, oracle):
 
 def test_warp_matches_plain_numpy(scene, oracle):
     """QueryFrameTransform in float64 numpy vs the oracle's fp32 tree-ordered evaluation."""
-    from f2nerf_b200.scene import view_trans
+    from synth_scene import view_trans
     o, d, dn, _ = make_rays(scene, 16)
     noise = np.ones(1024 + 16 + 10, np.float32)
     s = oracle.sampler(scene["nodes"], scene["trans"], o, dn, noise, 0.05, 1e8, 1 / 256, False, 1024)
@@ -179,7 +179,7 @@ def test_octree_votes_small(oracle):
     vw, va, mk = oracle.mark_visit(b, oct_idx, 1, w, a, 5, vc)
     assert vw.tolist() == [-1, -1, 512, -1, -1] and va.tolist() == [-1, -1, -1, 32, -1]
     assert mk.tolist() == [0, 0, 1, 1, 0] and vc.tolist() == [0, 0, 2, 3, 0]
-    from f2nerf_b200.scene import TREE_NODE, to_bytes, view_nodes
+    from synth_scene import TREE_NODE, to_bytes, view_nodes
     nodes = np.zeros(5, TREE_NODE); nodes["trans_idx"] = np.arange(5)
     blob = to_bytes(nodes)
     sw, sa = np.array([1000, 0, 0, 0, 5], np.int32), np.array([1000, 0, 0, 0, 5], np.int32)
@@ -189,7 +189,7 @@ def test_octree_votes_small(oracle):
 
 
 def test_scene_builder_is_consistent(scene):
-    from f2nerf_b200.scene import view_edges, view_nodes, view_trans
+    from synth_scene import view_edges, view_nodes, view_trans
     nodes, trans, edges = view_nodes(scene["nodes"]), view_trans(scene["trans"]), view_edges(scene["edges"])
     valid = nodes[nodes["trans_idx"] >= 0]
     assert len(trans) == len(valid) > 10 and len(edges) > 0
