@@ -143,14 +143,20 @@ def build_problem(rank, world, args, device):
                 ray_gen=None if sb["synthetic"] is not None else prob_gen)
 
 
-def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None):
-    """ExpRunner::Train's use of the path (src/ExpRunner.cpp:93-130) minus the optimizer step."""
+def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None, next_rays=None):
+    """ExpRunner::Train's use of the path (src/ExpRunner.cpp:93-130) minus the optimizer step.  ``next_rays``: the
+    (rays_o, rays_d) the NEXT call will be given (or a callable producing them — the e2e loop uploads them here): their
+    march is software-pipelined behind this step's loss + backward (Renderer.prefetch_next); every step still runs exactly
+    one march."""
     import torch
     from f2nerf_b200 import CustomOps
     r = prob["renderer"]
     for p in (prob["field"].feat_pool_, prob["field"].mlp_.params_, prob["shader"].mlp_.params_, r.app_emb_):
         p.grad = None
     res = r.Render(rays_o, rays_d, None, emb_idx)
+    if next_rays is not None:
+        nxt = next_rays() if callable(next_rays) else next_rays
+        r.prefetch_next(nxt[0], nxt[1])
     color_loss = torch.sqrt((res.colors - gt) ** 2 + 1e-4).mean()
     var_loss = torch.sqrt(CustomOps.WeightVar(res.weights, res.idx_start_end) + 1e-2).mean()
     tv_loss = ((res.edge_feats[:, 0] - res.edge_feats[:, 1]) ** 2).mean()
@@ -232,8 +238,9 @@ def run_ours(args):
     # ---- device-resident timing (value): K steps bracketed by barrier + synchronize, CUDA events --------
     clocks = ClockSampler(local)                 # polling starts before the warm-up: the first NVML queries of a
     clocks.start()                               # process stall kernel submission for 100s of ms on this driver
+    nxt = (d_o, d_d) if args.pipeline_march else None           # the same resident batch every step: the next rays are these
     for _ in range(args.warmup):                 # same object lifetimes as the timed loop (the caching allocator must have
-        loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)   # seen the steady-state peak before timing starts)
+        loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync, nxt)   # seen the steady-state peak before timing starts)
     barrier()
     clocks.rows.clear()                          # keep only samples taken under the timed regions
     def timed_loop():
@@ -254,7 +261,7 @@ def run_ours(args):
         w = []
         for _ in range(args.steps):
             w0 = time.perf_counter()
-            loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
+            loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync, nxt)
             ns += prob["renderer"].n_sampled_pts_
             nk += res.weights.shape[0]
             w.append(round((time.perf_counter() - w0) * 1e3, 2))
@@ -278,17 +285,26 @@ def run_ours(args):
     # ---- per-kernel CUDA-event trace over the same steps (separate loop: event pairs around every C-ABI call) --
     _lib.TRACE = []
     for _ in range(args.steps):
-        train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync)
+        train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync, nxt)
     barrier()
     trace, _lib.TRACE = _lib.TRACE, None
     # ---- end-to-end timing: pinned host rays -> device, loss -> host, every step ----------------
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    up = lambda: (h_o.to(device, non_blocking=True), h_d.to(device, non_blocking=True))
+    prob["renderer"].pts_sampler_.take_prefetched(d_o, d_d)       # drop the resident loop's pending prefetch
+    ro, rd = up()                                                 # pipeline fill (outside the timed region, like the warm-up)
+    barrier()
     e2.record()
-    for _ in range(args.steps):
-        ro, rd = h_o.to(device, non_blocking=True), h_d.to(device, non_blocking=True)
-        rc, rg = h_cam.to(device, non_blocking=True), h_gt.to(device, non_blocking=True)
-        loss, res = train_step(prob, ro, rd, rc, rg, dist_sync)
+    for _ in range(args.steps):                                   # per step: ONE upload of a ray batch (the next step's when the march
+        rc, rg = h_cam.to(device, non_blocking=True), h_gt.to(device, non_blocking=True)   # is pipelined), cam + gt of this step
+        if args.pipeline_march:
+            box = []
+            loss, res = train_step(prob, ro, rd, rc, rg, dist_sync, lambda: box.append(up()) or box[0])
+            ro, rd = box[0]
+        else:
+            loss, res = train_step(prob, ro, rd, rc, rg, dist_sync)
+            ro, rd = up()
         loss_host = float(loss.item())
     e3.record()
     barrier()
@@ -587,6 +603,8 @@ def main():
     ap.add_argument("--config", default="wanjinyou", choices=sorted(W.CONFIGS))
     ap.add_argument("--rays", type=int, default=0, help="override the config's ray count (global for strong-scaling configs)")
     ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=0, help="--impl reference: rays per step (0 = sized to ~2 min total)")
+    ap.add_argument("--no-pipeline-march", dest="pipeline_march", action="store_false",
+                    help="march every batch at the start of its own Render (default: the next batch's march runs behind this step's backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()

@@ -15,6 +15,7 @@
 //   acc = w001*f001; acc = fma(w000,f000,acc); then fma in order 010,011,100,101,110,111.
 #include "common.cuh"
 #include "hash.cuh"
+#include <stdlib.h>
 
 namespace f2b {
 
@@ -46,14 +47,14 @@ hash_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_p
 // grad*128, Hash3DAnchored.cu:145-151, and casts/divides afterwards); zero-gradient rows are skipped (:149).
 constexpr int kDirectHeads = 24;
 
+// The grid is PERSISTENT and bounded (ctas_per_sm x SM count CTAs striding over the (32 samples, level) tasks): a few resident
+// warps per SM already saturate the reduction pipe, and a bounded grid lets the scatter of one ray chunk run on a side stream
+// next to the tcgen05 kernels of the next chunk without crowding their CTAs out (an unbounded grid of 260 k small blocks did).
 template <bool GRAD_F16>
-__global__ void __launch_bounds__(256)
-hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bias_pool, int n_volumes,
-                int local_size, const float* __restrict__ pts, const int* __restrict__ vol,
-                int vol_stride, int n_pts, const void* __restrict__ grad_feat, float grad_mul,
-                float* __restrict__ grad_table) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_id = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void hash_bwd_task(int64_t warp_id, int lane, const int* __restrict__ prim_pool,
+                                              const float* __restrict__ bias_pool, int n_volumes, int local_size,
+                                              const float* __restrict__ pts, const int* __restrict__ vol, int vol_stride, int n_pts,
+                                              const void* __restrict__ grad_feat, float grad_mul, float* __restrict__ grad_table) {
   const int l = int(warp_id & 15);
   const int64_t i = (warp_id >> 4) * 32 + lane;
   const bool valid = i < n_pts;
@@ -124,6 +125,19 @@ hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bia
   }
 }
 
+template <bool GRAD_F16>
+__global__ void __launch_bounds__(256)
+hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bias_pool, int n_volumes,
+                int local_size, const float* __restrict__ pts, const int* __restrict__ vol,
+                int vol_stride, int n_pts, const void* __restrict__ grad_feat, float grad_mul,
+                float* __restrict__ grad_table, int64_t n_tasks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += stride)
+    hash_bwd_task<GRAD_F16>(w, lane, prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, n_pts, grad_feat, grad_mul,
+                            grad_table);
+}
+
 __global__ void level_scales_kernel(float* out) {
   if (threadIdx.x < F2B_N_LEVELS) out[threadIdx.x] = level_scale(threadIdx.x);
 }
@@ -161,12 +175,18 @@ extern "C" int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_
                             void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(prim_pool && bias_pool && pts && vol && grad_feat && grad_table, "f2b_hash_bwd: null pointer");
-  const int blocks = div_up(int64_t(div_up(n_pts, 32)) * 16 * 32, 256);    // one warp per (32 samples, level)
+  const int64_t n_tasks = int64_t(div_up(n_pts, 32)) * 16;                 // one warp-task per (32 samples, level)
+  static int ctas_per_sm = -1;                                             // resident 256-thread CTAs per SM (F2B_SCATTER_CTAS, default 8 = all)
+  if (ctas_per_sm < 0) { const char* e = getenv("F2B_SCATTER_CTAS"); ctas_per_sm = e ? atoi(e) : 8; if (ctas_per_sm < 1) ctas_per_sm = 1; }
+  int sms = 148;
+  f2b_device_info(&sms, nullptr);
+  const int64_t want = div_up(n_tasks * 32, int64_t(256));
+  const int blocks = int(want < int64_t(sms) * ctas_per_sm ? want : int64_t(sms) * ctas_per_sm);
   if (grad_is_f16)
     hash_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts,
-                                                                 vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table);
+                                                                 vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table, n_tasks);
   else
     hash_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts,
-                                                                  vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table);
+                                                                  vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table, n_tasks);
   return check_launch("f2b_hash_bwd");
 }

@@ -64,7 +64,14 @@ class Renderer:
         n_rays, dev = rays_o.shape[0], rays_o.device
         train = gdp.mode_ == TRAIN
         # ---- phase 1: march -> early-stop field pass -> survivors, in the march's slot layout (no host sync) ----
-        slots = sampler.begin_march(rays_o, rays_d)                  # draws the ray noise (RNG order: noise, bg, ...)
+        pf = sampler.take_prefetched(rays_o, rays_d) if n_rays > 0 else None
+        if pf is not None:                                           # marched during the previous backward (prefetch_next)
+            slots = pf["slots"]
+            gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+            gen.set_offset(gen.get_offset() + pf["noise_inc"])       # the noise draw happened ahead of time (same numbers)
+            torch.cuda.current_stream(dev).wait_event(pf["done"])
+        else:
+            slots = sampler.begin_march(rays_o, rays_d)              # draws the ray noise (RNG order: noise, bg, ...)
         self.sample_result_ = LazySampleResult(slots)                # the reference-layout view, built only on access
         bg = self._bg(n_rays, dev)
         if n_rays <= 0:
@@ -91,7 +98,8 @@ class Renderer:
                 if st is not main:                                   # pass (memory latency) overlaps chunk k+1's march (issue)
                     st.wait_event(ready)
                 with torch.cuda.stream(st):
-                    sampler.march_rays(slots, r0, r1)
+                    if pf is None:
+                        sampler.march_rays(slots, r0, r1)
                     ops.field_fwd_slots(table16, field.prim_pool_, field.bias_pool_, field.n_volumes_, field.local_size_,
                                         fparams16, slots.s_pts[r0 * S:r1 * S], slots.s_anchors[r0 * S:r1 * S],
                                         slots.counts[r0:r1], r1 - r0, S, logit_s[r0 * S:r1 * S], feat_s[r0 * S:r1 * S])
@@ -162,6 +170,19 @@ class Renderer:
         if side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)      # joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, es.first_oct_dis, disparity, edge_feats, depth, weights, new_bounds)
+
+    def prefetch_next(self, rays_o, rays_d):
+        """Software-pipeline the NEXT batch's ray march behind this batch's loss + backward.  Call right after ``Render``
+        returned (TRAIN mode), with the ray tensors the next ``Render`` will be given: the march reads no trainable state, only
+        the octree as this iteration's votes leave it, so it is queued on the votes' side stream and its ~1 ms of per-ray
+        dependent latency disappears from the critical path.  Results are bit-identical to an unpipelined run (same noise
+        numbers, same octree state); a next ``Render`` with different rays simply ignores the prefetch."""
+        gdp = self.global_data_pool_
+        dev = rays_o.device
+        pending = ()
+        if gdp.gradient_scaling_progress_ < 1. and getattr(self, "n_kept_pts_", 0) > 0:      # the coming backward's burns
+            pending = (self.n_kept_pts_ * 3, self.n_kept_pts_)
+        self.pts_sampler_.prefetch_march(rays_o, rays_d, self._side_stream(dev, 1), pending)
 
     def _side_stream(self, dev, i=1):
         pool = self.__dict__.setdefault("_streams_", {})

@@ -134,10 +134,10 @@ class PersSampler:
         return self.materialize(slots)
 
     # ---- slot-layout pieces (used by Renderer.Render; GetSamples = begin_march + march_rays + materialize) ----------
-    def begin_march(self, rays_o_raw, rays_d_raw, rays_noise=None):
+    def begin_march(self, rays_o_raw, rays_d_raw, rays_noise=None, normalised=False):
         """Normalise directions, draw the noise (PersSampler.cu:373-380) and bind the scratch; launches no march yet."""
         rays_o = rays_o_raw.contiguous()
-        rays_d = (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
+        rays_d = rays_d_raw if normalised else (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
         n_rays = rays_o.shape[0]
         if rays_noise is None:
             rays_noise = self.make_noise(n_rays, rays_o.device)
@@ -158,6 +158,56 @@ class PersSampler:
              slots.counts[r0:r1], slots.chunk_bounds[r0:r1], totals, slots.first_oct_dis[r0:r1], stream())
         call("f2b_slot_bounds", slots.counts[r0:r1], n, S, r0, slots.slot_bounds[r0:r1], stream())
         slots.totals.append(totals)
+
+    # ---- software pipelining of the march (it reads no trainable state: only rays, noise and the octree) ------------------
+    def prefetch_march(self, rays_o_raw, rays_d_raw, stream, pending_rand_numel=()):
+        """March the NEXT batch now, on ``stream`` (a side stream that already carries this iteration's octree votes, so the
+        march sees the pruned tree exactly as a march issued at the start of the next ``Render`` would), while the caller's
+        main stream runs loss + backward of the current batch.  The next ``begin_march`` with the same ray tensors picks the
+        result up instead of marching.
+
+        RNG-stream parity: the noise is drawn from the Philox position it will have when the next Render starts —
+        ``pending_rand_numel`` lists the ``torch.rand`` sizes still to be consumed before then (the GradientScaling burns of
+        the coming backward) — and the generator is then put back, so a prefetched run draws the very same numbers as an
+        unpipelined one under the same seed."""
+        from .rng import rand_philox_offset
+        dev = rays_o_raw.device
+        main = torch.cuda.current_stream(dev)
+        n_rays = rays_o_raw.shape[0]
+        gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        here = gen.get_offset()
+        ahead = sum(rand_philox_offset(int(n), dev) for n in pending_rand_numel)
+        gen.set_offset(here + ahead)
+        noise = self.make_noise(n_rays, dev)                       # drawn on the main stream (tiny), consumed by the side stream
+        noise_inc = gen.get_offset() - (here + ahead)
+        gen.set_offset(here)
+        rays_o = rays_o_raw.contiguous()
+        rays_d = (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
+        slots = self.begin_march(rays_o, rays_d, noise, normalised=True)
+        ev = torch.cuda.Event()
+        ev.record(main)                                            # everything queued so far (compaction, votes' inputs) precedes the overwrite
+        stream.wait_event(ev)
+        with torch.cuda.stream(stream):
+            self.march_rays(slots, 0, n_rays)
+            done = torch.cuda.Event()
+            done.record(stream)
+        for t in (rays_o, rays_d, noise, slots.counts, slots.chunk_bounds, slots.slot_bounds, slots.first_oct_dis, *slots.totals):
+            t.record_stream(stream)
+        self._prefetched = dict(key=(rays_o_raw.data_ptr(), rays_d_raw.data_ptr(), n_rays, rays_o_raw._version, rays_d_raw._version),
+                                slots=slots, done=done, noise_inc=noise_inc, tree=self.tree_nodes_gpu_.data_ptr(),
+                                mode=self.global_data_pool_.mode_, fineness=self.global_data_pool_.ray_march_fineness_)
+
+    def take_prefetched(self, rays_o_raw, rays_d_raw):
+        """The prefetched march for exactly these ray tensors (and an unchanged octree / mode / fineness), or None."""
+        pf, self._prefetched = getattr(self, "_prefetched", None), None
+        if pf is None:
+            return None
+        gdp = self.global_data_pool_
+        key = (rays_o_raw.data_ptr(), rays_d_raw.data_ptr(), rays_o_raw.shape[0], rays_o_raw._version, rays_d_raw._version)
+        if (key != pf["key"] or pf["tree"] != self.tree_nodes_gpu_.data_ptr() or pf["mode"] != gdp.mode_
+                or pf["fineness"] != gdp.ray_march_fineness_ or pf["slots"].generation != getattr(self, "_generation", 0)):
+            return None
+        return pf
 
     def note_totals(self, n_rays, n_all_oct):
         """EMA of octree intersections per ray (PersSampler.cu:378-379); called once the host knows the totals."""

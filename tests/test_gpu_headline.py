@@ -11,7 +11,7 @@ oracle/ref_driver.cpp sets them.
 Bars: every integer / index output and the sampler's fp32 outputs bit-exact; per-ray fp32 outputs within 1e-4 relative of
 their scale given the same keep mask (rays whose T > 1e-4 crossing flipped — MUFU vs libm exp on a threshold-straddling
 sample — are compared on their counts only); gradients: global relative L2 error and cosine against the oracle's
-fp32-accumulate chain (the same fp16 rounding points), thresholds ~3x what the B200 measured (gpurun_out/headline_*.json).
+fp32-accumulate chain (the same fp16 rounding points), within 3e-4 (north_star: 1e-4 relative fp32; measured 4e-6 .. 1e-4, gpurun_out/headline_*.json).
 """
 import json
 import os
@@ -117,9 +117,12 @@ def test_train_step_at_config_matches_oracle(oracle, cfg_name, n_rays):
     json.dump(stats, open(os.path.join(ROOT, "gpurun_out", f"headline_{cfg_name}.json"), "w"), indent=1)
     # composite is downstream of the fp16 MLP outputs: one flipped fp16 rounding of a density logit moves a ray's colour by
     # ~1e-3 of its weight; the bars below are per-ray maxima over 4096 rays
-    assert stats["colors_max_rel_same_mask"] <= 5e-3 and stats["colors_median_rel"] <= 1e-4, stats
-    assert stats["depth_median_rel"] <= 1e-4 and stats["disparity_median_rel"] <= 1e-4, stats
-    assert abs(stats["loss"] - stats["loss_oracle"]) <= 1e-4 * abs(stats["loss_oracle"]), stats
+    # measured on B200 (round 2): colours max 5e-4 / median 9e-7 of scale, depth / disparity max 1.2e-4 / median 4e-7, loss 8e-7,
+    # gradient rel-L2 4e-6 .. 1e-4 (cosine 1 - 5e-9): the bars sit ~3x above those
+    assert stats["colors_max_rel_same_mask"] <= 2e-3 and stats["colors_median_rel"] <= 1e-5, stats
+    assert stats["depth_max_rel_same_mask"] <= 5e-4 and stats["disparity_max_rel_same_mask"] <= 5e-4, stats
+    assert stats["depth_median_rel"] <= 1e-5 and stats["disparity_median_rel"] <= 1e-5, stats
+    assert abs(stats["loss"] - stats["loss_oracle"]) <= 1e-5 * abs(stats["loss_oracle"]), stats
     for name, _ in pairs:
-        assert stats[name]["cos"] >= 0.9999 and stats[name]["rel_l2"] <= 1e-2, (name, stats[name])
+        assert stats[name]["cos"] >= 1 - 1e-7 and stats[name]["rel_l2"] <= 3e-4, (name, stats[name])
     assert np.abs(ref["grad_feat_pool"]).max() > 0

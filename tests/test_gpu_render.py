@@ -73,8 +73,14 @@ def test_render_train_step_matches_oracle(scene, oracle, n_rays, gs_progress):
     assert_close(N(res.colors), ref["colors"], rtol=2e-3, atol_frac=2e-3, name="colors")
     assert_close(N(res.disparity), ref["disparity"], rtol=2e-3, atol_frac=2e-3, name="disparity")
     assert_close(N(res.depth), ref["depth"], rtol=2e-3, atol_frac=2e-3, name="depth")
-    assert abs(float(loss) - ref["loss"]) <= 2e-3 * abs(ref["loss"])
-    # gradients (fp16 MLP chain in between: fp16-level tolerance relative to the tensor's scale)
+    assert abs(float(loss) - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+    # gradients.  Globally (relative L2 against the oracle's fp32-accumulate chain with the same fp16 rounding points) they
+    # agree to ~1e-5 (measured on B200, cf. tests/test_gpu_headline.py); element-wise a single flipped fp16 rounding shows,
+    # hence the looser per-element bars below
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / (np.linalg.norm(b) + 1e-300))
+    for name, mine in (("grad_field_mlp", field.mlp_.params_.grad), ("grad_shader_mlp", shader.mlp_.params_.grad),
+                       ("grad_app_emb", renderer.app_emb_.grad), ("grad_feat_pool", field.feat_pool_.grad)):
+        assert rel(N(mine), np.asarray(ref[name], np.float64)) <= 1e-3, (name, rel(N(mine), np.asarray(ref[name], np.float64)))
     assert_close(N(field.mlp_.params_.grad), ref["grad_field_mlp"], rtol=2e-2, atol_frac=1e-2, name="grad field mlp")
     assert_close(N(shader.mlp_.params_.grad), ref["grad_shader_mlp"], rtol=2e-2, atol_frac=1e-2, name="grad shader mlp")
     assert_close(N(renderer.app_emb_.grad), ref["grad_app_emb"], rtol=2e-2, atol_frac=1e-2, name="grad app_emb")
@@ -167,3 +173,41 @@ def test_operator_level_autograd(scene, oracle):
     (rgb.sum() + out[:, 0].sum()).backward()
     for p in (field.feat_pool_, field.mlp_.params_, shader.mlp_.params_):
         assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("gs_progress", [1.0, 0.3])
+def test_prefetched_march_equals_unpipelined(scene, gs_progress):
+    """Renderer.prefetch_next (the next batch's march queued behind this batch's backward, on the octree-vote stream) must not
+    change a single bit: same noise numbers (drawn ahead from the right Philox position, incl. the GradientScaling burns of
+    the pending backward), same pruned octree, same outputs and gradients over three consecutive TRAIN steps; a prefetch for
+    rays that are not the ones rendered next is ignored."""
+    from f2nerf_b200 import TRAIN
+    batches = [make_rays(scene, n, seed=40 + i) for i, n in enumerate((150, 97, 150))]
+    outs = []
+    for pipelined in (False, True):
+        gdp, sampler, field, shader, renderer = build(scene)
+        gdp.mode_, gdp.gradient_scaling_progress_ = TRAIN, gs_progress
+        torch.manual_seed(2024)
+        dev_batches = [(T(o), T(d), T(cam)) for o, d, dn, cam in batches]
+        rec = []
+        for i, (ro, rd, cam) in enumerate(dev_batches):
+            for p in (field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_):
+                p.grad = None
+            r = renderer.Render(ro, rd, None, cam)
+            if pipelined and i + 1 < len(dev_batches):
+                renderer.prefetch_next(dev_batches[i + 1][0], dev_batches[i + 1][1])
+            if pipelined and i + 1 == len(dev_batches):
+                renderer.prefetch_next(dev_batches[0][0], dev_batches[0][1])          # never consumed by a matching Render
+            loss = (r.colors ** 2).mean() + r.disparity.mean() + 0.1 * ((r.edge_feats[:, 0] - r.edge_feats[:, 1]) ** 2).mean()
+            loss.backward()
+            rec += [N(r.colors), N(r.weights), N(r.idx_start_end), N(r.first_oct_dis), N(sampler.tree_weight_stats_),
+                    N(shader.mlp_.params_.grad), N(renderer.app_emb_.grad)]
+        # one more Render with rays the pending prefetch was NOT made for
+        r = renderer.Render(dev_batches[1][0], dev_batches[1][1], None, dev_batches[1][2])
+        rec += [N(r.colors), N(r.idx_start_end)]
+        outs.append(rec)
+    for k, (a, b) in enumerate(zip(*outs)):
+        if a.dtype == np.float32 and k % 7 in (5, 6) and k < 21:      # atomically accumulated gradients: summation order only
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7 * np.abs(a).max())
+        else:
+            np.testing.assert_array_equal(a, b, err_msg=str(k))

@@ -11,7 +11,7 @@ from conftest import make_rays
 
 
 def test_struct_layouts_match_reference_bytes():
-    from f2nerf_b200 import scene as S
+    import synth_scene as S
     assert S.TREE_NODE.itemsize == 64 and S.TRANS_INFO.itemsize == 544 and S.EDGE_POOL.itemsize == 64
     assert S.TREE_NODE.fields["childs"][1] == 20 and S.TREE_NODE.fields["trans_idx"][1] == 56
     assert S.TRANS_INFO.fields["weight"][1] == 384 and S.TRANS_INFO.fields["dis_summary"][1] == 540
