@@ -223,8 +223,10 @@ def run_ours(args):
     prob = build_problem(rank, world, args, device)
     n_rays = prob["n_rays"]                                     # rays THIS rank renders per step
     if world > 1:
-        from f2nerf_b200.dist import install_vote_sync
+        from f2nerf_b200.dist import install_grad_overlap, install_vote_sync
         install_vote_sync(prob["sampler"])
+        if os.environ.get("F2B_DP_OVERLAP", "1") == "1":
+            install_grad_overlap(prob["renderer"])                # table-gradient all-reduce per level slab, behind the scatter
     o, d, cam, gt = prob["host"]
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h_o, h_d, h_cam, h_gt = pin(o), pin(d), pin(cam), pin(gt)

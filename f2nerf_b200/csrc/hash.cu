@@ -51,12 +51,11 @@ constexpr int kDirectHeads = 24;
 // warps per SM already saturate the reduction pipe, and a bounded grid lets the scatter of one ray chunk run on a side stream
 // next to the tcgen05 kernels of the next chunk without crowding their CTAs out (an unbounded grid of 260 k small blocks did).
 template <bool GRAD_F16>
-__device__ __forceinline__ void hash_bwd_task(int64_t warp_id, int lane, const int* __restrict__ prim_pool,
+__device__ __forceinline__ void hash_bwd_task(int64_t group, int l, int lane, const int* __restrict__ prim_pool,
                                               const float* __restrict__ bias_pool, int n_volumes, int local_size,
                                               const float* __restrict__ pts, const int* __restrict__ vol, int vol_stride, int n_pts,
                                               const void* __restrict__ grad_feat, float grad_mul, float* __restrict__ grad_table) {
-  const int l = int(warp_id & 15);
-  const int64_t i = (warp_id >> 4) * 32 + lane;
+  const int64_t i = group * 32 + lane;
   const bool valid = i < n_pts;
   float g0 = 0.f, g1 = 0.f;
   if (valid) {
@@ -130,12 +129,13 @@ __global__ void __launch_bounds__(256)
 hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bias_pool, int n_volumes,
                 int local_size, const float* __restrict__ pts, const int* __restrict__ vol,
                 int vol_stride, int n_pts, const void* __restrict__ grad_feat, float grad_mul,
-                float* __restrict__ grad_table, int64_t n_tasks) {
+                float* __restrict__ grad_table, int64_t n_tasks, int level_lo, int log2_levels) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int lmask = (1 << log2_levels) - 1;
   for (int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += stride)
-    hash_bwd_task<GRAD_F16>(w, lane, prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, n_pts, grad_feat, grad_mul,
-                            grad_table);
+    hash_bwd_task<GRAD_F16>(w >> log2_levels, level_lo + int(w & lmask), lane, prim_pool, bias_pool, n_volumes, local_size, pts, vol,
+                            vol_stride, n_pts, grad_feat, grad_mul, grad_table);
 }
 
 __global__ void level_scales_kernel(float* out) {
@@ -169,13 +169,21 @@ extern "C" int f2b_hash_fwd(const void* table_f16, const int* prim_pool, const f
   return check_launch("f2b_hash_fwd");
 }
 
-extern "C" int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
-                            const float* pts, const int* vol, int vol_stride, int n_pts,
-                            const void* grad_feat, int grad_is_f16, float grad_mul, float* grad_table,
-                            void* stream) {
+// Levels [level_lo, level_lo + n_levels) only (n_levels a power of two).  Level l writes the fp32 slab
+// [l*local_size, (l+2)*local_size) of grad_table (the half-overlapping level layout, Hash3DAnchored.cu:37), so once the groups
+// above and including level l have run, everything from float (l+1)*local_size upwards is final: a data-parallel host launches
+// the groups top-down and starts the all-reduce of each finished slab while the next group still scatters (f2nerf_b200/dist.py).
+extern "C" int f2b_hash_bwd_levels(const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
+                                   const float* pts, const int* vol, int vol_stride, int n_pts,
+                                   const void* grad_feat, int grad_is_f16, float grad_mul, float* grad_table,
+                                   int level_lo, int n_levels, void* stream) {
   if (n_pts <= 0) return F2B_OK;
   F2B_REQUIRE(prim_pool && bias_pool && pts && vol && grad_feat && grad_table, "f2b_hash_bwd: null pointer");
-  const int64_t n_tasks = int64_t(div_up(n_pts, 32)) * 16;                 // one warp-task per (32 samples, level)
+  F2B_REQUIRE(n_levels > 0 && (n_levels & (n_levels - 1)) == 0 && level_lo >= 0 && level_lo + n_levels <= F2B_N_LEVELS,
+              "f2b_hash_bwd_levels: n_levels must be a power of two and the range inside [0,16)");
+  int log2_levels = 0;
+  while ((1 << log2_levels) < n_levels) log2_levels++;
+  const int64_t n_tasks = int64_t(div_up(n_pts, 32)) * n_levels;           // one warp-task per (32 samples, level)
   static int ctas_per_sm = -1;                                             // resident 256-thread CTAs per SM (F2B_SCATTER_CTAS, default 8 = all)
   if (ctas_per_sm < 0) { const char* e = getenv("F2B_SCATTER_CTAS"); ctas_per_sm = e ? atoi(e) : 8; if (ctas_per_sm < 1) ctas_per_sm = 1; }
   int sms = 148;
@@ -183,10 +191,18 @@ extern "C" int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_
   const int64_t want = div_up(n_tasks * 32, int64_t(256));
   const int blocks = int(want < int64_t(sms) * ctas_per_sm ? want : int64_t(sms) * ctas_per_sm);
   if (grad_is_f16)
-    hash_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts,
-                                                                 vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table, n_tasks);
+    hash_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride,
+                                                                 n_pts, grad_feat, grad_mul, grad_table, n_tasks, level_lo, log2_levels);
   else
-    hash_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts,
-                                                                  vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table, n_tasks);
+    hash_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride,
+                                                                  n_pts, grad_feat, grad_mul, grad_table, n_tasks, level_lo, log2_levels);
   return check_launch("f2b_hash_bwd");
+}
+
+extern "C" int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
+                            const float* pts, const int* vol, int vol_stride, int n_pts,
+                            const void* grad_feat, int grad_is_f16, float grad_mul, float* grad_table,
+                            void* stream) {
+  return f2b_hash_bwd_levels(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, n_pts, grad_feat, grad_is_f16, grad_mul,
+                             grad_table, 0, F2B_N_LEVELS, stream);
 }

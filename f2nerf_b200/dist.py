@@ -29,6 +29,37 @@ def install_vote_sync(sampler):
     sampler.vote_allreduce_ = sync
 
 
+def install_grad_overlap(renderer):
+    """Overlap the table-gradient all-reduce with the scatter that produces it.  The renderer's backward then scatters per
+    level group, top-down (f2b_hash_bwd_levels), and calls the hook after each group; level l writes only floats
+    [l*S, (l+2)*S) of the gradient, so after the group starting at level ``lo`` everything from float (lo+1)*S up to the
+    previous boundary is final and its SUM all-reduce is issued at once (async, on NCCL's stream, ordered behind the scatter
+    stream) while the lower groups still run.  Only the last slab ([0, 5S) of 17S) is exposed.  The 1/world averaging is folded
+    into the scatter's gradient multiplier; the backward's last act is to make its stream wait for the slab all-reduces, so
+    the gradient autograd hands to ``.grad`` is already the global average and ``allreduce_grads`` skips the table."""
+    world = dist.get_world_size()
+    renderer.grad_premul_ = 1.0 / world
+    st = dict(hi=None, works=[], table=None)
+
+    def hook(d_table, level_lo, local_size):
+        flat = d_table.view(-1)
+        if level_lo == 12 or st["table"] is not d_table:                 # first group of this backward
+            st.update(hi=min(flat.numel(), 17 * local_size), works=[], table=d_table)
+        lo = (level_lo + 1) * local_size if level_lo > 0 else 0
+        if st["hi"] > lo:
+            st["works"].append(dist.all_reduce(flat[lo:st["hi"]], async_op=True))
+        st["hi"] = lo
+
+    def finish():
+        for w in st["works"]:
+            w.wait()                                                      # the current (main) stream waits; no host block
+        st.update(works=[], table=None)
+        renderer.table_grad_reduced_ = True
+
+    renderer.grad_slab_hook_, renderer.grad_slab_finish_ = hook, finish
+    renderer.table_grad_reduced_ = False
+
+
 def allreduce_grads(renderer):
     """The post-backward exchange step; returns the number of bytes each rank contributed.  Every rank issues the SAME
     fixed-shape collectives whether or not its own batch produced gradients (a rank whose rays all missed the octree
@@ -37,12 +68,16 @@ def allreduce_grads(renderer):
     field, shader = renderer.scene_field_, renderer.shader_
     params = (field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_)
     sent = 0
-    if field.feat_pool_.grad is None:
-        field.feat_pool_.grad = torch.zeros_like(field.feat_pool_)
-    g = field.feat_pool_.grad[:live_rows(field)]
-    dist.all_reduce(g)
-    g.div_(world)
-    sent += g.numel() * g.element_size()
+    if getattr(renderer, "table_grad_reduced_", False) and field.feat_pool_.grad is not None:
+        renderer.table_grad_reduced_ = False             # averaged slab by slab inside the backward (install_grad_overlap)
+        sent += live_rows(field) * 2 * 4
+    else:
+        if field.feat_pool_.grad is None:
+            field.feat_pool_.grad = torch.zeros_like(field.feat_pool_)
+        g = field.feat_pool_.grad[:live_rows(field)]
+        dist.all_reduce(g)
+        g.div_(world)
+        sent += g.numel() * g.element_size()
     dev = field.feat_pool_.device
     flag = getattr(renderer, "nonfinite_flag_", None)
     flag = torch.zeros(2, device=dev) if flag is None else flag.reshape(-1).float().expand(2) if flag.numel() == 1 else flag.float()

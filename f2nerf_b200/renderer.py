@@ -341,12 +341,22 @@ class _RenderFunction(torch.autograd.Function):
         bounds = es.pts_idx_bounds
         hash_args = (field.prim_pool_, field.bias_pool_, int(field.n_volumes_), int(field.local_size_))
 
+        # Data parallel: ``grad_slab_hook_`` (f2nerf_b200.dist.install_grad_overlap) wants the table gradient slab by slab, so that
+        # the NCCL all-reduce of a finished slab runs while the lower level groups still scatter.  Level l only writes floats
+        # [l*S, (l+2)*S): the scatter then runs per level group, top-down, after the dense chain; the hook is called after each.
+        slab_hook = getattr(renderer, "grad_slab_hook_", None)
+        grad_mul = (1.0 / f_scale) * (getattr(renderer, "grad_premul_", 1.0) if slab_hook is not None else 1.0)
+        jobs = []
+
         def scatter(pts, anc, stride, s0, s1):            # on the side stream, behind everything queued on main so far
+            if slab_hook is not None:
+                jobs.append((pts, anc, stride, s0, s1))
+                return
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                ops.hash_bwd(*hash_args, pts, anc, stride, dfeat16[s0:s1], 1.0 / f_scale, d_table)
+                ops.hash_bwd(*hash_args, pts, anc, stride, dfeat16[s0:s1], grad_mul, d_table)
 
         for r0, r1, s0, s1 in ctx.cuts:
             if s1 <= s0:
@@ -369,7 +379,19 @@ class _RenderFunction(torch.autograd.Function):
                      f_hidden[1, first:first + rows] if nh_f else None, fparams16, int(nh_f), rows,
                      dfeat16[first:first + rows], d_fparams, stream())
                 scatter(pts_e, anc_e, stride_e, first, first + rows)
+        if slab_hook is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for lo in (12, 8, 4, 0):
+                    for pts_j, anc_j, stride_j, s0, s1 in jobs:
+                        call("f2b_hash_bwd_levels", *hash_args, pts_j, anc_j, int(stride_j), int(s1 - s0), dfeat16[s0:s1], 1, float(grad_mul),
+                             d_table, lo, 4, stream())
+                    slab_hook(d_table, lo, int(field.local_size_))          # issued on the side stream: NCCL orders itself behind it
         main.wait_stream(side)
+        if slab_hook is not None:
+            renderer.grad_slab_finish_()                  # the main stream waits for the slab all-reduces: d_table leaves here averaged
         d_sparams = d_sparams / s_scale
         d_fparams = d_fparams / f_scale
         # NaN back-off of TCNNWPFunction::backward (TCNNWP.cpp:231-240): the reference tests dL/dparams AND dL/dinput of

@@ -191,8 +191,8 @@ class PersSampler:
             self.march_rays(slots, 0, n_rays)
             done = torch.cuda.Event()
             done.record(stream)
-        for t in (rays_o, rays_d, noise, slots.counts, slots.chunk_bounds, slots.slot_bounds, slots.first_oct_dis, *slots.totals):
-            t.record_stream(stream)
+        # no record_stream: every tensor the side stream touches stays referenced from the prefetch record / the slots until the
+        # consuming Render has made the main stream wait on ``done``, so it cannot be recycled under the march
         self._prefetched = dict(key=(rays_o_raw.data_ptr(), rays_d_raw.data_ptr(), n_rays, rays_o_raw._version, rays_d_raw._version),
                                 slots=slots, done=done, noise_inc=noise_inc, tree=self.tree_nodes_gpu_.data_ptr(),
                                 mode=self.global_data_pool_.mode_, fineness=self.global_data_pool_.ray_march_fineness_)
@@ -206,6 +206,7 @@ class PersSampler:
         key = (rays_o_raw.data_ptr(), rays_d_raw.data_ptr(), rays_o_raw.shape[0], rays_o_raw._version, rays_d_raw._version)
         if (key != pf["key"] or pf["tree"] != self.tree_nodes_gpu_.data_ptr() or pf["mode"] != gdp.mode_
                 or pf["fineness"] != gdp.ray_march_fineness_ or pf["slots"].generation != getattr(self, "_generation", 0)):
+            torch.cuda.current_stream(rays_o_raw.device).wait_event(pf["done"])      # its buffers are released behind the march
             return None
         return pf
 

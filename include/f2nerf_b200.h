@@ -120,6 +120,13 @@ int f2b_hash_bwd(const int* prim_pool, const float* bias_pool, int n_volumes, in
                  const float* pts, const int* vol, int vol_stride, int n_pts,
                  const void* grad_feat, int grad_is_f16, float grad_mul,
                  float* grad_table, void* stream);
+/* f2b_hash_bwd restricted to levels [level_lo, level_lo + n_levels), n_levels a power of two.  Level l only writes floats
+ * [l*local_size, (l+2)*local_size) of grad_table, so a data-parallel host can launch level groups top-down and all-reduce each
+ * finished slab (everything from float (level_lo+1)*local_size upwards) while the lower groups still scatter. */
+int f2b_hash_bwd_levels(const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
+                        const float* pts, const int* vol, int vol_stride, int n_pts,
+                        const void* grad_feat, int grad_is_f16, float grad_mul, float* grad_table,
+                        int level_lo, int n_levels, void* stream);
 
 /* MLP (no biases, ReLU hidden, linear out padded to 16): params_f16 = [W0 64xin | (W_h 64x64)*n_hidden_matmuls | W_out 16x64],
  * each row-major [out][in] (fully_fused_mlp.cu:654-677).  in: [P,32] fp16.  out: [P,16] fp16.

@@ -45,11 +45,21 @@ def _worker(rank, world, port, q):
     mk = torch.tensor([1, 1, 0, 0], dtype=torch.int32) if rank == 0 else torch.tensor([0, 0, 1, 0], dtype=torch.int32)
     vc = torch.tensor([3, 7, 0, 0], dtype=torch.int32) if rank == 0 else torch.tensor([0, 9, 4, 0], dtype=torch.int32)
     sampler.vote_allreduce_(vw, va, mk, vc)
+    # slab-wise overlapped all-reduce of the table gradient (install_grad_overlap): the hook sequence the backward issues
+    fd.install_grad_overlap(renderer)
+    assert renderer.grad_premul_ == 0.5
+    gs = torch.Generator().manual_seed(100 + rank)
+    slab = torch.rand(pool, 2, generator=gs)
+    slab0 = slab.clone()
+    for lo in (12, 8, 4, 0):
+        renderer.grad_slab_hook_(slab, lo, local)
+    renderer.grad_slab_finish_()
+    assert renderer.table_grad_reduced_
     gdp = GlobalDataPool()
     gdp.sampled_pts_per_ray_ = 100.0 + 50 * rank
     fd.sync_emas(gdp)
     q.put((rank, [t.numpy() for t in mine], [t.numpy() for t in got], renderer.nonfinite_flag_.tolist(), sent,
-           vw.tolist(), va.tolist(), mk.tolist(), vc.tolist(), gdp.sampled_pts_per_ray_))
+           vw.tolist(), va.tolist(), mk.tolist(), vc.tolist(), gdp.sampled_pts_per_ray_, slab0.numpy(), slab.numpy()))
     dist.destroy_process_group()
 
 
@@ -73,3 +83,7 @@ def test_allreduce_step_world2():
     assert v0[0] == v1[0] == [-1, 512, 512, -1] and v0[1] == v1[1] == [32, -1, -1, -1]
     assert v0[2] == v1[2] == [1, 1, 1, 0] and v0[3] == v1[3] == [3, 9, 4, 0]
     assert abs(v0[4] - 125.0) < 1e-9 and v0[4] == v1[4]
+    live = 17 * 256 // 2                                                # slabs cover exactly the live prefix, once each
+    np.testing.assert_allclose(v0[6][:live], v0[5][:live] + v1[5][:live], rtol=1e-6)
+    np.testing.assert_array_equal(v0[6][:live], v1[6][:live])
+    np.testing.assert_array_equal(v0[6][live:], v0[5][live:])

@@ -211,3 +211,32 @@ def test_prefetched_march_equals_unpipelined(scene, gs_progress):
             np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7 * np.abs(a).max())
         else:
             np.testing.assert_array_equal(a, b, err_msg=str(k))
+
+
+def test_render_whole_image_matches_oracle(oracle):
+    """N4: RenderWholeImage on rays of a reference ngp_fox camera (the committed fixture's blobs / cameras, the reference's
+    parameter state) against the ORACLE's VALIDATE-mode forward of the same rays (noise == 1, background 0.5): sampler integers
+    bit-exact upstream, colours / disparity within 1e-4 of scale given the same keep mask, the reference's normalisations
+    (ExpRunner.cpp:289-290) applied on top."""
+    import bench
+    import oracle_pipeline as OP
+    import workloads as W
+    from types import SimpleNamespace
+    from f2nerf_b200 import RenderWholeImage, ops
+    n_rays = 3000                                                    # ragged against the 1024-ray chunks used below
+    prob = bench.build_problem(0, 1, SimpleNamespace(config="wanjinyou", rays=n_rays), torch.device("cuda", 0))
+    cfg, field, shader, renderer = prob["cfg"], prob["field"], prob["shader"], prob["renderer"]
+    o, d, cam, _ = prob["host"]
+    pc, fo, pd = RenderWholeImage(renderer, torch.from_numpy(o), torch.from_numpy(d), None, ray_batch_size=1024)
+    dn = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    dn = N(T(d) / torch.linalg.norm(T(d), 2, -1, True))            # the device's normalisation (what the sampler sees)
+    sc = dict(nodes=prob["blobs"][0], trans=prob["blobs"][1], edges=prob["blobs"][2], near=cfg["near"], sample_l=cfg["sample_l"],
+              scale_by_dis=cfg["scale_by_dis"], max_hits=1024)
+    fld = dict(table16=N(field.table_f16()), prim=N(field.prim_pool_), bias=N(field.bias_pool_), V=field.n_volumes_,
+               local_size=field.local_size_, mlp_params=N(field.mlp_.params_))
+    ref = OP.render_train(sc, o, dn, np.ones(1024 + n_rays + 10, np.float32), np.full((n_rays, 3), .5, np.float32), fld,
+                          N(shader.mlp_.params_), None, None, None, None, scales=ops.hash_level_scales().numpy())
+    colors, disp, first = ref["colors"], ref["disparity"].reshape(-1, 1), ref["sample"]["first_oct_dis"].reshape(-1, 1)
+    assert np.abs(N(pc) - colors).max() <= 2e-3 and np.median(np.abs(N(pc) - colors)) <= 1e-5
+    np.testing.assert_allclose(N(pd), disp / disp.max(), rtol=0, atol=5e-4)
+    np.testing.assert_array_equal(N(fo), (first.min() / first).astype(np.float32))
