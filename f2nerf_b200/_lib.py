@@ -47,6 +47,7 @@ SIGNATURES = {
     "f2b_hash_level_scales": [_P],
     "f2b_table_to_half": [_P, _P, c_i64, _P],
     "f2b_hash_fwd": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P],
+    "f2b_hash_fwd_levels": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "f2b_hash_bwd": [_P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
     "f2b_hash_bwd_levels": [_P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_float, _P, c_int, c_int, _P],
     "f2b_mlp_fwd": [_P, _P, c_int, c_int, _P, _P, _P],

@@ -38,6 +38,30 @@ hash_fwd_kernel(const __half* __restrict__ table, const int* __restrict__ prim_p
   for (int q = 0; q < 4; q++) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 }
 
+// Encode of a level range only (out rows keep their [P,32] layout; other levels' columns are not written): used to attribute
+// the encode's time to level groups (scripts/level_probe.py, profiles/r02_level_probe.md) and by callers that refresh a subset.
+__global__ void __launch_bounds__(128)
+hash_fwd_levels_kernel(const __half* __restrict__ table, const int* __restrict__ prim_pool,
+                       const float* __restrict__ bias_pool, int n_volumes, int local_size,
+                       const float* __restrict__ pts, const int* __restrict__ vol, int vol_stride, int n_pts,
+                       int level_lo, int n_levels, __half* __restrict__ out) {
+  __shared__ float s_scale[F2B_N_LEVELS];
+  if (threadIdx.x < F2B_N_LEVELS) s_scale[threadIdx.x] = level_scale(threadIdx.x);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const float p0 = __ldg(pts + size_t(i) * 3), p1 = __ldg(pts + size_t(i) * 3 + 1), p2 = __ldg(pts + size_t(i) * 3 + 2);
+  const float x0 = fmul(fadd(p0, 1.f), .5f), x1 = fmul(fadd(p1, 1.f), .5f), x2 = fmul(fadd(p2, 1.f), .5f);
+  const int v = __ldg(vol + size_t(i) * vol_stride);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + size_t(i) * 32);
+  for (int l = level_lo; l < level_lo + n_levels; l++) {
+    const int tv = l * n_volumes + v;
+    Corner8 c;
+    corners(x0, x1, x2, s_scale[l], prim_pool + tv * 3, bias_pool + tv * 3, (unsigned)local_size, c);
+    dst[l] = encode_level(table, l, local_size, c);
+  }
+}
+
 // Backward: a warp owns 32 CONSECUTIVE samples at one level (samples of a ray are consecutive, so at the
 // coarse levels many lanes fall into the same grid cell and hit the same 8 table entries).  Lanes are grouped
 // into runs of identical (cell, volume); when the warp has few runs, the 16 per-run sums (8 corners x 2
@@ -167,6 +191,19 @@ extern "C" int f2b_hash_fwd(const void* table_f16, const int* prim_pool, const f
       (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, n_pts,
       (__half*)out_f16);
   return check_launch("f2b_hash_fwd");
+}
+
+extern "C" int f2b_hash_fwd_levels(const void* table_f16, const int* prim_pool, const float* bias_pool,
+                                   int n_volumes, int local_size, const float* pts, const int* vol,
+                                   int vol_stride, int n_pts, int level_lo, int n_levels, void* out_f16, void* stream) {
+  if (n_pts <= 0) return F2B_OK;
+  F2B_REQUIRE(table_f16 && prim_pool && bias_pool && pts && vol && out_f16, "f2b_hash_fwd_levels: null pointer");
+  F2B_REQUIRE(n_volumes > 0 && local_size > 0 && (local_size % 2) == 0, "f2b_hash_fwd_levels: bad n_volumes/local_size");
+  F2B_REQUIRE(level_lo >= 0 && n_levels > 0 && level_lo + n_levels <= F2B_N_LEVELS, "f2b_hash_fwd_levels: level range outside [0,16)");
+  hash_fwd_levels_kernel<<<div_up(n_pts, 128), 128, 0, as_stream(stream)>>>(
+      (const __half*)table_f16, prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride, n_pts, level_lo, n_levels,
+      (__half*)out_f16);
+  return check_launch("f2b_hash_fwd_levels");
 }
 
 // Levels [level_lo, level_lo + n_levels) only (n_levels a power of two).  Level l writes the fp32 slab

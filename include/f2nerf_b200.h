@@ -112,6 +112,11 @@ int f2b_hash_fwd(const void* table_f16, const int* prim_pool, const float* bias_
                  int n_volumes, int local_size,
                  const float* pts, const int* vol, int vol_stride, int n_pts,
                  void* out_f16, void* stream);
+/* f2b_hash_fwd for levels [level_lo, level_lo + n_levels) only: writes columns 2*l, 2*l+1 of those levels into out [P,32] and
+ * leaves the rest untouched (per-level attribution of the encode's cost, partial refreshes). */
+int f2b_hash_fwd_levels(const void* table_f16, const int* prim_pool, const float* bias_pool,
+                        int n_volumes, int local_size, const float* pts, const int* vol,
+                        int vol_stride, int n_pts, int level_lo, int n_levels, void* out_f16, void* stream);
 /* Backward: grad_feat [P,32] (fp16 when grad_is_f16, else fp32; dL/d encoded features), each value
  * multiplied by grad_mul (e.g. 1/loss_scale), scattered into grad_table [pool_size,2] fp32 (zeroed by
  * the caller) with red.global.add.v2.f32 — instead of the reference's fp16 atomicAdd(__half2) of

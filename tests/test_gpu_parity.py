@@ -723,3 +723,34 @@ def test_octree_mark_invisible_matches_oracle(scene, oracle):
         np.testing.assert_array_equal(N(sampler.tree_nodes_gpu_), want.reshape(-1))
     ti = want.view(np.int32).reshape(-1, 16)[:, 14]
     assert (ti < 0).all()
+
+
+def test_hash_level_range_entry_points(scene, oracle, hash_params):
+    """f2b_hash_fwd_levels / f2b_hash_bwd_levels: the level groups, run one after the other, reproduce the full encode bit for
+    bit and the full scatter to fp32 summation order; a group touches only its own output columns / its own table slab
+    [lo*S, (lo+n+1)*S)."""
+    from f2nerf_b200 import ops
+    from f2nerf_b200._lib import call, stream
+    hp = hash_params
+    rng = np.random.default_rng(3)
+    n = 5000
+    pts = T((rng.random((n, 3), dtype=np.float32) * 2 - 1))
+    vol = T(rng.integers(0, hp["V"], n).astype(np.int32))
+    table, prim, bias = T(hp["table"]), T(hp["prim"]), T(hp["bias"])
+    full = ops.hash_fwd(table, prim, bias, hp["V"], hp["local_size"], pts, vol, 1)
+    out = torch.full((n, 32), float("nan"), dtype=torch.float16, device=DEV)
+    for lo, nl in ((0, 4), (4, 4), (8, 8)):
+        call("f2b_hash_fwd_levels", table, prim, bias, hp["V"], hp["local_size"], pts, vol, 1, n, lo, nl, out, stream())
+        assert torch.isnan(out[:, 2 * (lo + nl):]).all()
+    np.testing.assert_array_equal(N(out).view(np.uint16), N(full).view(np.uint16))
+    g = T((rng.standard_normal((n, 32)) * 0.01).astype(np.float16))
+    S = hp["local_size"]
+    want = torch.zeros((hp["pool"], 2), device=DEV)
+    ops.hash_bwd(prim, bias, hp["V"], S, pts, vol, 1, g, 0.5, want)
+    got = torch.zeros((hp["pool"], 2), device=DEV)
+    for lo in (12, 8, 4, 0):
+        before = got.clone()
+        call("f2b_hash_bwd_levels", prim, bias, hp["V"], S, pts, vol, 1, n, g, 1, 0.5, got, lo, 4, stream())
+        changed = (got != before).view(-1).nonzero().view(-1)
+        assert changed.numel() > 0 and int(changed.min()) >= lo * S and int(changed.max()) < (lo + 5) * S
+    np.testing.assert_allclose(N(got), N(want), rtol=1e-5, atol=1e-7)
