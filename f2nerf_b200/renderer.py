@@ -63,6 +63,9 @@ class Renderer:
         field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
         n_rays, dev = rays_o.shape[0], rays_o.device
         train = gdp.mode_ == TRAIN
+        if self._fused_launch_ok(n_rays):
+            return self._render_fused_launches(rays_o, rays_d, emb_idx)
+        # ---- the same pipeline, one C-ABI call per kernel (per-kernel tracing, the CUDA-core MLP twin, ray / backward chunking)
         # ---- phase 1: march -> early-stop field pass -> survivors, in the march's slot layout (no host sync) ----
         pf = sampler.take_prefetched(rays_o, rays_d) if n_rays > 0 else None
         if pf is not None:                                           # marched during the previous backward (prefetch_next)
@@ -171,6 +174,118 @@ class Renderer:
             torch.cuda.current_stream(dev).wait_stream(side)      # joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, es.first_oct_dis, disparity, edge_feats, depth, weights, new_bounds)
 
+    # ------------------------------------------------------------------------------------------
+    def _fused_launch_ok(self, n_rays):
+        """One foreign call per phase (f2b_render_phase1 / _phase2_fwd / _bwd, csrc/render.cu) instead of one per kernel: the
+        default.  The per-kernel path stays for per-kernel tracing (bench.py's breakdown), the CUDA-core MLP twin and the
+        experimental ray / backward chunking."""
+        if n_rays <= 0 or _lib.TRACE is not None or os.environ.get("F2B_FUSED_LAUNCH", "1") != "1":
+            return False
+        if _lib.lib.f2b_get_mlp_impl() != 1 or self.scene_field_.mlp_.n_hidden_matmuls != 0 or self.shader_.mlp_.n_hidden_matmuls != 1:
+            return False
+        return len(self._ray_chunks(n_rays)) == 1 and self._bwd_cut_rays(n_rays) is None
+
+    def _render_fused_launches(self, rays_o, rays_d, emb_idx):
+        """Renderer::Render (Renderer.cpp:52-213): identical kernels, order, streams and RNG draws as the per-kernel path below,
+        issued through the three launch sequences of csrc/render.cu."""
+        gdp = self.global_data_pool_
+        field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
+        n_rays, dev = rays_o.shape[0], rays_o.device
+        train = gdp.mode_ == TRAIN
+        main = torch.cuda.current_stream(dev)
+        grad_on = torch.is_grad_enabled() and train                  # as the CALLER has it (everything up to the node is grad-free)
+        pf = sampler.take_prefetched(rays_o, rays_d)
+        if pf is not None:                                           # marched during the previous backward (prefetch_next)
+            slots = pf["slots"]
+            gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+            gen.set_offset(gen.get_offset() + pf["noise_inc"])       # the noise draw happened ahead of time (same numbers)
+            main.wait_event(pf["done"])
+        else:
+            slots = sampler.begin_march(rays_o, rays_d)              # draws the ray noise (RNG order: noise, bg, ...)
+        self.sample_result_ = LazySampleResult(slots)
+        bg = self._bg(n_rays, dev)
+        S = slots.slot
+        with torch.no_grad():
+            table16 = field.table_f16()
+            i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device=dev)
+            f16 = lambda *sh: torch.empty(sh, dtype=torch.float16, device=dev)
+            f32 = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+            fparams16, sparams16 = f16(field.mlp_.params_.numel()), f16(shader.mlp_.params_.numel())
+            logit_s = self._buf("logit", (n_rays * S,), torch.float32, dev)
+            feat_s = self._buf("feat", (n_rays * S, 32), torch.float16, dev)
+            weights0 = self._buf("w0", (n_rays * S,), torch.float32, dev)
+            alphas0 = self._buf("a0", (n_rays * S,), torch.float32, dev)
+            keep = self._buf("keep", (n_rays * S,), torch.uint8, dev)
+            kept_counts = self._buf("kept", (n_rays,), torch.int32, dev)
+            new_bounds, heads = i32(n_rays, 2), i32(3)                # heads = [n_kept, n_all, n_all_oct]
+            ra = _lib.RenderArgs()
+            ra.set(tree_nodes=sampler.tree_nodes_gpu_, n_nodes=sampler.n_nodes, trans=sampler.pers_trans_gpu_,
+                   n_trans=sampler.pers_trans_gpu_.numel() // 544, edge_pool=sampler.edge_pool_gpu_ if sampler.n_edges else None,
+                   near_t=float(sampler.global_near_), far_t=1e8, sample_l=float(sampler.sample_l_),
+                   scale_by_dis=int(sampler.scale_by_dis_), max_hits=int(sampler.max_oct_intersect_per_ray_),
+                   count_all_hits=int(bool(sampler.exact_oct_stat_)),
+                   table16=table16, prim=field.prim_pool_, bias=field.bias_pool_, n_volumes=int(field.n_volumes_),
+                   local_size=int(field.local_size_), field_params=field.mlp_.params_.detach(), n_field_params=fparams16.numel(),
+                   shader_params=shader.mlp_.params_.detach(), n_shader_params=sparams16.numel(), fparams16=fparams16,
+                   sparams16=sparams16, n_rays=n_rays, rays_o=slots.rays_o, rays_d=slots.rays_d, noise=slots.noise, bg=bg,
+                   skip_march=int(pf is not None), s_pts=slots.s_pts, s_dt=slots.s_dt, s_t=slots.s_t, s_anchors=slots.s_anchors,
+                   counts=slots.counts, chunk_bounds=slots.chunk_bounds, slot_bounds=slots.slot_bounds,
+                   first_oct_dis=slots.first_oct_dis, totals=heads[1:], logit_s=logit_s, feat_s=feat_s, w0=weights0, a0=alphas0,
+                   keep=keep, kept_counts=kept_counts, new_bounds=new_bounds, total_kept=heads, stream=stream())
+            if pf is not None:
+                heads[1:].copy_(slots.totals[0])                      # the prefetched march's own totals
+            call("f2b_render_phase1", ra)
+            if pf is not None:
+                _lib.LAUNCHES -= 3                                    # march (2 kernels) + slot bounds ran with the prefetch
+            n_kept, n_all, n_all_oct = heads.tolist()                 # THE host sync of the step
+            self._bwd_cuts_ = None
+            sampler.note_totals(n_rays, n_all_oct)
+            slots.noted = True
+            slots.totals = [heads[1:]]
+            self.n_sampled_pts_, self.n_kept_pts_ = n_all, n_kept
+            if train:
+                gdp.sampled_pts_per_ray_ = gdp.sampled_pts_per_ray_ * .9 + (n_all / n_rays) * .1
+            if n_all <= 0:
+                if train:
+                    gdp.meaningful_sampled_pts_per_ray_ *= .9
+                z = torch.zeros
+                return RenderResult(bg, z((n_rays, 1), device=dev), z((n_rays,), device=dev), None,
+                                    torch.full((n_rays,), 512., device=dev), None, None)
+            burn_mlp_output(n_all, dev)                   # RNG parity: the reference's MLP output is a torch::rand (rng.py)
+            side = None
+            if train:
+                side = self._side_stream(dev, 1)          # octree votes feed the NEXT march: beside the gradient pass
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sampler.update_oct_nodes_raw(slots.slot_bounds, slots.s_anchors, weights0, alphas0)
+                gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
+            n_pairs = N_EDGE_PTS if train else 0
+            n_edge = 2 * n_pairs
+            T = dict(pts=f32(n_kept, 3), dirs=f32(n_kept, 3), dt=f32(n_kept), t=f32(n_kept), anchors=i32(n_kept, 3),
+                     feat_q=f16(n_kept + n_edge, 32), logit=f32(n_kept), mlp_in=f16(n_kept, 32), raw=f16(n_kept, 16),
+                     rgb=f32(n_kept, 3), edge32=f32(n_edge, 16), colors=f32(n_rays, 3), disparity=f32(n_rays), depth=f32(n_rays),
+                     weights=f32(n_kept))
+            if grad_on:
+                T.update(f_hidden=f16(1, n_kept + n_edge, 64), s_hidden=f16(2, n_kept, 64))
+            if train:                                                                 # TV-loss edge points: the reference's draws
+                if sampler.n_edges <= 0:
+                    raise RuntimeError("GetEdgeSamples: empty edge pool (needs >= 2 face-adjacent valid leaves)")
+                T.update(edge_idx=torch.randint(0, sampler.n_edges, (n_pairs,), dtype=torch.int32, device=dev),
+                         edge_coord=torch.rand((n_pairs, 2), dtype=torch.float32, device=dev) * 2. - 1.,
+                         e_pts=f32(n_edge, 3), e_anc=i32(n_edge))
+            burn_mlp_output(n_kept + n_edge, dev)         # second AnchoredQuery (Renderer.cpp:165/172) ...
+            burn_mlp_output(n_kept, dev)                  # ... and the shader MLP (SHShader.cpp:27)
+            if train and self.use_app_emb_:
+                T.update(ray_emb_idx=emb_idx.to(torch.int32).contiguous(), pt_emb_idx=i32(n_kept))
+                ra.set(app_emb=self.app_emb_.detach(), n_emb=self.app_emb_.shape[0])
+            ra.set(n_kept=n_kept, n_edge_pairs=n_pairs, **T)
+            keepalive = (slots, table16, fparams16, sparams16, new_bounds, heads, bg, T)
+        colors, disparity, depth, weights, edge_feats = _FusedRenderFunction.apply(
+            field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, self, ra, keepalive, grad_on)
+        if side is not None:
+            main.wait_stream(side)                                # joined before weights0 / alphas0 can be recycled
+        return RenderResult(colors, slots.first_oct_dis.clone(), disparity, edge_feats if train else None, depth, weights, new_bounds)
+
     def prefetch_next(self, rays_o, rays_d):
         """Software-pipeline the NEXT batch's ray march behind this batch's loss + backward.  Call right after ``Render``
         returned (TRAIN mode), with the ray tensors the next ``Render`` will be given: the march reads no trainable state, only
@@ -247,6 +362,83 @@ class Renderer:
     def Reset(self):
         self.scene_field_.Reset()
         self.shader_.Reset()
+
+
+class _FusedRenderFunction(torch.autograd.Function):
+    """Second half of Renderer::Render (Renderer.cpp:127-208) with its whole backward, each ONE launch sequence of csrc/render.cu.
+    ``ra`` (the filled f2b_render block) and the tensors it points to travel in ``keepalive``."""
+
+    @staticmethod
+    def forward(ctx, feat_pool, field_params, shader_params, app_emb, renderer, ra, keepalive, grad_on):
+        T = keepalive[-1]
+        call("f2b_render_phase2_fwd", ra)
+        if ra.n_edge_pairs == 0:
+            _lib.LAUNCHES -= 3
+        ctx.renderer, ctx.ra, ctx.keepalive, ctx.grad_on = renderer, ra, keepalive, grad_on
+        ctx.gs_progress = renderer.global_data_pool_.gradient_scaling_progress_
+        ctx.table_shape, ctx.emb_shape = feat_pool.shape, app_emb.shape
+        return T["colors"], T["disparity"], T["depth"], T["weights"], T["edge32"].reshape(-1, 2, 16)
+
+    @staticmethod
+    def backward(ctx, d_colors, d_disp, d_depth, d_weights, d_edge):
+        renderer, ra = ctx.renderer, ctx.ra
+        if ctx.keepalive is None:
+            raise RuntimeError("Renderer.Render backward: the saved activations were released by a previous backward "
+                               "(like tiny-cuda-nn's context, TCNNWP.cpp:207, the graph can be traversed once)")
+        if not ctx.grad_on:
+            raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
+        field, shader = renderer.scene_field_, renderer.shader_
+        T = ctx.keepalive[-1]
+        dev = T["colors"].device
+        n_kept, n_edge, n_rays = ra.n_kept, 2 * ra.n_edge_pairs, ra.n_rays
+        main = torch.cuda.current_stream(dev)
+        c = lambda g: None if g is None else g.contiguous()
+        d_colors = c(d_colors) if d_colors is not None else torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
+        d_disp, d_depth, d_weights = c(d_disp), c(d_depth), c(d_weights)
+        d_edge = None if d_edge is None else d_edge.reshape(-1, 16).contiguous()
+        if ctx.gs_progress < 1.:                          # GradientScaling::backward draws an unused rand_like (CustomOps.cu:154)
+            burn_rand(n_kept * 3, dev)
+            burn_rand(n_kept, dev)
+        f16 = lambda *sh: torch.empty(sh, dtype=torch.float16, device=dev)
+        f32 = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        emb_on = "ray_emb_idx" in T
+        slab_hook = getattr(renderer, "grad_slab_hook_", None)
+        f_scale = field.mlp_.loss_scale_
+        grad_mul = (1.0 / f_scale) * (getattr(renderer, "grad_premul_", 1.0) if slab_hook is not None else 1.0)
+        B = dict(d_logit=f32(n_kept), d_raw=f16(n_kept, 16), d_in16=f16(n_kept, 32), d_scene16=f16(n_kept + n_edge, 16),
+                 dfeat16=f16(n_kept + n_edge, 32), d_sparams=f32(ra.n_shader_params), d_fparams=f32(ra.n_field_params),
+                 d_table=torch.empty(ctx.table_shape, dtype=torch.float32, device=dev),
+                 nonfinite=torch.empty((2,), dtype=torch.int32, device=dev))
+        if emb_on:
+            B["d_app"] = torch.empty(ctx.emb_shape, dtype=torch.float32, device=dev)
+        side = renderer._side_stream(dev, 2)
+        ra.set(d_colors=d_colors, d_disparity=d_disp, d_depth=d_depth, d_weights=d_weights, d_edge=d_edge,
+               gs_progress=float(ctx.gs_progress), shader_loss_scale=float(shader.mlp_.loss_scale_), field_loss_scale=float(f_scale),
+               table_grad_mul=float(grad_mul), table_numel=B["d_table"].numel(),
+               table_live=min(B["d_table"].numel(), 17 * int(field.local_size_)), scatter_mode=int(slab_hook is not None),
+               stream=main.cuda_stream, side_stream=side.cuda_stream, **B)
+        call("f2b_render_bwd", ra)
+        if slab_hook is not None:                         # data parallel: level slabs top-down, all-reduce of each behind it (dist.py)
+            hash_args = (field.prim_pool_, field.bias_pool_, int(field.n_volumes_), int(field.local_size_))
+            jobs = [(T["pts"], T["anchors"], 3, 0, n_kept)] + ([(T["e_pts"], T["e_anc"], 1, n_kept, n_kept + n_edge)] if n_edge else [])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for lo in (12, 8, 4, 0):
+                    for pts_j, anc_j, stride_j, s0, s1 in jobs:
+                        if s1 > s0:
+                            call("f2b_hash_bwd_levels", *hash_args, pts_j, anc_j, int(stride_j), int(s1 - s0), B["dfeat16"][s0:s1], 1,
+                                 float(grad_mul), B["d_table"], lo, 4, stream())
+                    slab_hook(B["d_table"], lo, int(field.local_size_))
+            main.wait_stream(side)
+            renderer.grad_slab_finish_()
+        call("f2b_render_grad_finalize", ra)
+        bad = B["nonfinite"] != 0                          # [shader, field], device-side, no sync here
+        prev = getattr(renderer, "nonfinite_flag_", None)
+        renderer.nonfinite_flag_ = bad if prev is None else (prev | bad)
+        ctx.keepalive = None                              # saved activations die with the backward, not with `res`
+        return B["d_table"], B["d_fparams"], B["d_sparams"], B.get("d_app"), None, None, None, None
 
 
 class _RenderFunction(torch.autograd.Function):

@@ -340,6 +340,63 @@ int f2b_weight_var_fwd(const float* weights, const int* idx_start_end, int n_out
 int f2b_weight_var_bwd(const float* weights, const int* idx_start_end, int n_outs, const float* dl_dvars,
                        float* dl_dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Renderer::Render (src/Renderer/Renderer.cpp:52-213) as THREE launch sequences — what the host mirrors call per batch.
+ * Each entry point enqueues the fixed kernel sequence of one phase of the fused pipeline (the very kernels declared above,
+ * same order, same streams) in ONE call, so that a scripting-language host pays one foreign call per phase instead of one
+ * per kernel; nothing is allocated, every buffer (and the two streams) comes from the caller in `f2b_render`.  Fields a
+ * phase does not use may be left NULL / 0.  The host keeps what only it can do: the torch RNG draws (noise, background,
+ * edge indices / coordinates), the ONE host sync between phase 1 and phase 2 (n_kept sizes the survivors' buffers),
+ * the GlobalDataPool EMAs and the autograd plumbing.
+ *   f2b_render_phase1      [march + slot bounds unless skip_march] -> field-parameter cast -> early-stop field pass on the
+ *                          slots -> per-ray early stop -> survivor count scan                    (Renderer.cpp:52-126)
+ *   f2b_render_phase2_fwd  compaction -> [TRAIN: edge points + their encode] -> point->camera index -> parameter casts ->
+ *                          field MLP + shader-input epilogue -> edge-point MLP -> shader MLP + colour activation ->
+ *                          composite                                                             (Renderer.cpp:127-208)
+ *   f2b_render_bwd         zero-fills -> composite/activation bwd -> shader MLP bwd -> input-assembly bwd -> field MLP bwd
+ *                          (ray samples, edge points) -> [scatter_mode 0: hash scatter of both on side_stream, joined]
+ *   f2b_render_grad_finalize  un-scale the two MLP gradients (TCNNWP.cpp:225-229) and raise the per-MLP non-finite flags
+ *                          (dL/dparams, and dL/dinput through d_app / the live table gradient; TCNNWP.cpp:231-240)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct f2b_render {
+  /* scene blobs + sampler settings (PersSampler) */
+  const void* tree_nodes; int n_nodes; const void* trans; int n_trans; const void* edge_pool;
+  float near_t, far_t, sample_l; int scale_by_dis, max_hits, count_all_hits;
+  /* field / shader parameters: fp32 masters, fp16 copies written by phase1 (field) and phase2_fwd (both) */
+  const void* table16; const int* prim; const float* bias; int n_volumes, local_size;
+  const float* field_params; int n_field_params; const float* shader_params; int n_shader_params;
+  void* fparams16; void* sparams16;
+  const float* app_emb; int n_emb;                       /* NULL: no appearance embedding */
+  /* the ray batch */
+  int n_rays; const float* rays_o; const float* rays_d /* normalised */; const float* noise; const float* bg;
+  const int* ray_emb_idx;                                /* [n_rays] or NULL */
+  /* phase 1: slot layout (ray r owns slots [r*1024, r*1024 + counts[r])) */
+  int skip_march;                                        /* 1: the slots were marched ahead of time (prefetch) */
+  float* s_pts; float* s_dt; float* s_t; int* s_anchors; int* counts; int* chunk_bounds; int* slot_bounds;
+  float* first_oct_dis; int* totals /* [2] */;
+  float* logit_s; void* feat_s; float* w0; float* a0; uint8_t* keep; int* kept_counts; int* new_bounds; int* total_kept;
+  /* phase 2: survivors (n_kept rows) + TV-loss edge points (2 * n_edge_pairs rows behind them in feat_q / f_hidden / dfeat16) */
+  int n_kept; int n_edge_pairs;
+  float* pts; float* dirs; float* dt; float* t; int* anchors; void* feat_q;
+  const int* edge_idx; const float* edge_coord; float* e_pts; int* e_anc;
+  int* pt_emb_idx;                                       /* [n_kept] scratch, used when app_emb && ray_emb_idx */
+  float* logit; void* mlp_in; void* f_hidden /* nullable */; float* edge32; void* raw; float* rgb; void* s_hidden /* nullable */;
+  float* colors; float* disparity; float* depth; float* weights;
+  /* backward */
+  const float* d_colors; const float* d_disparity; const float* d_depth; const float* d_weights; const float* d_edge /* [2*pairs,16] */;
+  float gs_progress, shader_loss_scale, field_loss_scale, table_grad_mul;
+  float* d_logit; void* d_raw; void* d_in16; void* d_scene16; void* dfeat16;
+  float* d_sparams; float* d_fparams; float* d_table; int64_t table_numel; int64_t table_live; float* d_app;
+  int scatter_mode;                                      /* 0: scatter inside f2b_render_bwd; 1: the caller scatters (level slabs) */
+  int* nonfinite;                                        /* [2] device ints: shader MLP, field MLP */
+  void* stream; void* side_stream;
+} f2b_render;
+int f2b_render_sizeof(void);                 /* sizeof(f2b_render) as the library was built: bindings compare it with their own */
+int f2b_render_phase1(const f2b_render* r);
+int f2b_render_phase2_fwd(const f2b_render* r);
+int f2b_render_bwd(const f2b_render* r);
+int f2b_render_grad_finalize(const f2b_render* r);
+
 #ifdef __cplusplus
 }
 #endif
