@@ -92,6 +92,8 @@ SIGNATURES = {
     "f2b_flex_accumulate_sum": [_P, _P, c_int, c_int, _P, _P],
     "f2b_weight_var_fwd": [_P, _P, c_int, _P, _P],
     "f2b_weight_var_bwd": [_P, _P, c_int, _P, _P, _P],
+    "f2b_render_fwd_fused": [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
+    "f2b_gather_kept_weights": [_P, _P, c_int, c_int, _P, _P],
 }
 
 

@@ -91,5 +91,6 @@ extern "C" int f2b_mlp_bwd2(const void* dout_f16, const void* in_f16, const void
 #ifdef F2B_HAVE_TC
   if (mlp_bwd_impl() == 1) return f2b_mlp_bwd2_tc(dout_f16, in_f16, hidden0_f16, hidden1_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 #endif
+  if (!hidden0_f16 && n_pts > 0) { f2b::set_error("f2b_mlp_bwd2: recompute (hidden0 == NULL) needs the tcgen05 implementation"); return F2B_EUNSUPPORTED; }
   return f2b_mlp_bwd2_v0(dout_f16, in_f16, hidden0_f16, hidden1_f16, params_f16, n_hidden_matmuls, n_pts, din_f16, dparams_f32, stream);
 }

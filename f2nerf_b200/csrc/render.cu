@@ -97,7 +97,7 @@ extern "C" int f2b_render_phase2_fwd(const f2b_render* r) {
 
 extern "C" int f2b_render_bwd(const f2b_render* r) {
   F2B_REQUIRE(r, "f2b_render_bwd: null argument block");
-  F2B_REQUIRE(r->f_hidden && r->s_hidden, "f2b_render_bwd: the forward ran without saving activations");
+  // f_hidden / s_hidden NULL: the forward saved no hidden activations, f2b_mlp_bwd2 rebuilds them (recompute, tcgen05 only)
   const int64_t nk = r->n_kept, ne = 2 * int64_t(r->n_edge_pairs), nq = nk + ne;
   cudaStream_t st = as_stream(r->stream), side = as_stream(r->side_stream);
   const bool emb = r->app_emb && r->ray_emb_idx;
@@ -114,14 +114,14 @@ extern "C" int f2b_render_bwd(const f2b_render* r) {
     F2B_TRY(f2b_composite_act_bwd(r->logit, 1, r->rgb, r->dt, r->t, r->new_bounds, r->bg, r->n_rays, r->d_colors, r->d_disparity,
                                   r->d_depth, r->d_weights, r->gs_progress, r->raw, r->shader_loss_scale, r->d_logit, 1, r->d_raw,
                                   r->stream));
-    F2B_TRY(f2b_mlp_bwd2(r->d_raw, r->mlp_in, r->s_hidden, off(r->s_hidden, nk * 128), r->sparams16, 1, (int)nk, r->d_in16, r->d_sparams,
+    F2B_TRY(f2b_mlp_bwd2(r->d_raw, r->mlp_in, r->s_hidden, r->s_hidden ? off(r->s_hidden, nk * 128) : nullptr, r->sparams16, 1, (int)nk, r->d_in16, r->d_sparams,
                          r->stream));
     F2B_TRY(f2b_shader_prep_bwd_f16(r->d_in16, r->d_logit, r->new_bounds, emb ? r->ray_emb_idx : nullptr, r->n_rays,
                                     1.f / r->shader_loss_scale, r->field_loss_scale, r->d_scene16, emb ? r->d_app : nullptr, r->stream));
     F2B_TRY(f2b_mlp_bwd2(r->d_scene16, r->feat_q, r->f_hidden, nullptr, r->fparams16, 0, (int)nk, r->dfeat16, r->d_fparams, r->stream));
   }
   if (ne > 0)
-    F2B_TRY(f2b_mlp_bwd2(off(r->d_scene16, nk * 32), off(r->feat_q, nk * 64), off(r->f_hidden, nk * 128), nullptr, r->fparams16, 0, (int)ne,
+    F2B_TRY(f2b_mlp_bwd2(off(r->d_scene16, nk * 32), off(r->feat_q, nk * 64), r->f_hidden ? off(r->f_hidden, nk * 128) : nullptr, nullptr, r->fparams16, 0, (int)ne,
                          off(r->dfeat16, nk * 64), r->d_fparams, r->stream));
   if (r->scatter_mode != 0) return F2B_OK;
   // the scatter (L2 reductions) on the side stream behind the dense chain, joined before returning

@@ -6,6 +6,8 @@ into CPU tensors with ``index_put_`` — 3 blocking H2D + 3 blocking D2H copies 
 chunk.  Same chunking and the same returned tensors here (CPU ``pred_colors [N,3]``, ``first_oct_disp [N,1]``,
 ``pred_disp [N,1]`` with the reference's normalisations), but the rays are uploaded once (pinned, asynchronous), the
 per-chunk results are written straight into device-resident images, and there is ONE device->host copy at the end.
+Each chunk is the march + ONE fused kernel (``Renderer.render_forward`` -> ``f2b_render_fwd_fused``, csrc/fused_fwd.cu) writing its
+rows of the image; chunks alternate between two streams / scratch sets so a chunk's march runs under its predecessor's fused kernel.
 """
 import torch
 
@@ -36,13 +38,37 @@ def RenderWholeImage(renderer, rays_o, rays_d, bounds=None, ray_batch_size=RAY_B
     prev_mode = gdp.mode_
     gdp.mode_ = VALIDATE                                         # the reference's callers set it (ExpRunner.cpp:323,342)
     try:
-        for i in range(0, n_rays, ray_batch_size):
-            j = min(i + ray_batch_size, n_rays)
-            r = renderer.Render(o[i:j], d[i:j], None, None)
-            colors[i:j] = r.colors
-            disp[i:j, 0] = r.disparity.reshape(-1)
-            if r.first_oct_dis is not None and r.first_oct_dis.numel() == (j - i):
-                first[i:j] = r.first_oct_dis.reshape(-1, 1)
+        if renderer._fused_forward_ok(n_rays):
+            # Tiled renderer: every chunk is march + ONE fused kernel (Renderer.render_forward) that writes its rows of the
+            # device-resident image directly; no host sync, no per-chunk copies.  Two chunks are in flight on two streams with
+            # two march scratch sets, so chunk k+1's march (per-ray latency bound, ~20 % occupancy) runs under chunk k's
+            # fused kernel (gather bound).
+            main = torch.cuda.current_stream(dev)
+            lanes = [renderer._side_stream(dev, 3), renderer._side_stream(dev, 4)]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            disp_flat, depth = disp.view(-1), torch.empty((n_rays,), dtype=torch.float32, device=dev)
+            alive = []
+            for k, i in enumerate(range(0, n_rays, ray_batch_size)):
+                j = min(i + ray_batch_size, n_rays)
+                st = lanes[k % 2]
+                if k < 2:
+                    st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    r = renderer.render_forward(o[i:j], d[i:j], out=(colors[i:j], disp_flat[i:j], depth[i:j]), lane=1 + k % 2)
+                    first[i:j] = r.first_oct_dis.reshape(-1, 1)
+                alive.append(r)                                  # allocations of a lane stay referenced until the join below
+            for st in lanes:
+                main.wait_stream(st)
+            del alive
+        else:
+            for i in range(0, n_rays, ray_batch_size):
+                j = min(i + ray_batch_size, n_rays)
+                r = renderer.Render(o[i:j], d[i:j], None, None)
+                colors[i:j] = r.colors
+                disp[i:j, 0] = r.disparity.reshape(-1)
+                if r.first_oct_dis is not None and r.first_oct_dis.numel() == (j - i):
+                    first[i:j] = r.first_oct_dis.reshape(-1, 1)
     finally:
         gdp.mode_ = prev_mode
     disp = disp / disp.max()                                     # ExpRunner.cpp:289-290

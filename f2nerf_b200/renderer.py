@@ -20,6 +20,9 @@ from .rng import burn_mlp_output, burn_rand
 from .sampler import TRAIN, VALIDATE, LazySampleResult, SampleResultFlex
 
 N_EDGE_PTS = 8192
+# The tcgen05 MLP backward rebuilds the hidden activations from the 64 B input row instead of reading 128 / 256 B per sample the
+# forward saved (f2b_mlp_bwd2 with hidden0 == NULL): bit-identical dL/dinput, no hidden_save traffic.  F2B_MLP_RECOMPUTE=0 saves.
+MLP_RECOMPUTE = os.environ.get("F2B_MLP_RECOMPUTE", "1") == "1"
 
 
 @dataclass
@@ -32,6 +35,38 @@ class RenderResult:
     depth: torch.Tensor
     weights: Optional[torch.Tensor]
     idx_start_end: Optional[torch.Tensor]
+
+
+class ForwardRenderResult:
+    """``RenderResult`` of the fused forward-only path (``f2b_render_fwd_fused``): the per-ray fields are plain tensors; the two
+    per-sample fields the reference also returns — ``weights [P']`` and ``idx_start_end [R,2]`` (Renderer.h:24-25) — are packed
+    out of the kernel's slot-layout weights on first access (one scan, one 4-byte host read, one gather).  Nothing on the
+    evaluation path (ExpRunner::RenderWholeImage, ExpRunner.cpp:257-293) reads them."""
+    edge_feats = None
+
+    def __init__(self, colors, first_oct_dis, disparity, depth, kept_counts, w_slots, slot, owner, stamp):
+        self.colors, self.first_oct_dis, self.disparity, self.depth = colors, first_oct_dis, disparity, depth
+        self.kept_counts = kept_counts
+        self._w_slots, self._slot, self._owner, self._stamp, self._packed = w_slots, slot, owner, stamp, None
+
+    def _pack(self):
+        if self._packed is None:
+            if self._owner._fwd_stamp.get(self._stamp[0]) != self._stamp[1]:
+                raise RuntimeError("RenderResult.weights: a later Render re-used this result's slot-layout weights")
+            n_rays, dev = self.kept_counts.shape[0], self.kept_counts.device
+            bounds, total = ops.count_scan(self.kept_counts, n_rays)
+            w = torch.empty((int(total.item()),), dtype=torch.float32, device=dev)
+            call("f2b_gather_kept_weights", self._w_slots, bounds, n_rays, int(self._slot), w, stream())
+            self._packed = (w, bounds)
+        return self._packed
+
+    @property
+    def weights(self):
+        return self._pack()[0]
+
+    @property
+    def idx_start_end(self):
+        return self._pack()[1]
 
 
 class Renderer:
@@ -63,6 +98,8 @@ class Renderer:
         field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
         n_rays, dev = rays_o.shape[0], rays_o.device
         train = gdp.mode_ == TRAIN
+        if not train and self._fused_forward_ok(n_rays):
+            return self.render_forward(rays_o, rays_d)
         if self._fused_launch_ok(n_rays):
             return self._render_fused_launches(rays_o, rays_d, emb_idx)
         # ---- the same pipeline, one C-ABI call per kernel (per-kernel tracing, the CUDA-core MLP twin, ray / backward chunking)
@@ -265,7 +302,7 @@ class Renderer:
                      feat_q=f16(n_kept + n_edge, 32), logit=f32(n_kept), mlp_in=f16(n_kept, 32), raw=f16(n_kept, 16),
                      rgb=f32(n_kept, 3), edge32=f32(n_edge, 16), colors=f32(n_rays, 3), disparity=f32(n_rays), depth=f32(n_rays),
                      weights=f32(n_kept))
-            if grad_on:
+            if grad_on and not MLP_RECOMPUTE:
                 T.update(f_hidden=f16(1, n_kept + n_edge, 64), s_hidden=f16(2, n_kept, 64))
             if train:                                                                 # TV-loss edge points: the reference's draws
                 if sampler.n_edges <= 0:
@@ -285,6 +322,46 @@ class Renderer:
         if side is not None:
             main.wait_stream(side)                                # joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, slots.first_oct_dis.clone(), disparity, edge_feats if train else None, depth, weights, new_bounds)
+
+    def _fused_forward_ok(self, n_rays):
+        """VALIDATE mode takes no gradient, no occupancy votes and no TV-loss edge points: march + ONE kernel
+        (f2b_render_fwd_fused).  F2B_FUSED_FORWARD=0 (or per-kernel tracing / the CUDA-core MLP twin) keeps the operator pipeline."""
+        if n_rays <= 0 or _lib.TRACE is not None or os.environ.get("F2B_FUSED_FORWARD", "1") != "1":
+            return False
+        return (_lib.lib.f2b_get_mlp_impl() == 1 and self.scene_field_.mlp_.n_hidden_matmuls == 0
+                and self.shader_.mlp_.n_hidden_matmuls == 1)
+
+    def render_forward(self, rays_o, rays_d, out=None, lane=0):
+        """Renderer::Render (Renderer.cpp:52-213) for a batch that takes no gradient (VALIDATE mode): the march, then hash encode
+        -> field MLP -> early stop -> SH + shader MLP -> composite in ONE kernel that walks each ray front to back and stops at
+        the first opaque sample (csrc/fused_fwd.cu).  No host sync, no per-sample tensor in HBM; values bit-identical to the
+        operator pipeline.  ``out`` = (colors [R,3], disparity [R], depth [R]) views to write into (whole-image rendering writes
+        its image buffers directly); ``lane`` > 0 uses that extra scratch set so two chunks can be in flight on two streams.
+        Not reproduced: the reference's torch::rand draws for the MLP outputs (rng.py) — their sizes would need the host sync."""
+        field, shader, sampler = self.scene_field_, self.shader_, self.pts_sampler_
+        n_rays, dev = rays_o.shape[0], rays_o.device
+        slots = sampler.begin_march(rays_o, rays_d, lane=lane)
+        sampler.march_rays(slots, 0, n_rays)
+        if lane == 0:
+            self.sample_result_ = LazySampleResult(slots)
+        bg = self._bg(n_rays, dev)
+        S = slots.slot
+        with torch.no_grad():
+            table16 = field.table_f16()
+            fparams16, sparams16 = field.mlp_.params_f16(), shader.mlp_.params_f16()
+            f32 = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+            colors, disparity, depth = out if out is not None else (f32(n_rays, 3), f32(n_rays), f32(n_rays))
+            kept = torch.empty((n_rays,), dtype=torch.int32, device=dev)
+            ticket = torch.empty((1,), dtype=torch.int32, device=dev)
+            w_slots = self._buf(f"w_fwd{lane}", (n_rays * S,), torch.float32, dev)
+            stamps = self.__dict__.setdefault("_fwd_stamp", {})
+            stamps[lane] = stamps.get(lane, 0) + 1
+            call("f2b_render_fwd_fused", table16, field.prim_pool_, field.bias_pool_, int(field.n_volumes_), int(field.local_size_),
+                 fparams16, sparams16, slots.s_pts, slots.s_dt, slots.s_t, slots.s_anchors, slots.counts, slots.rays_d, bg, n_rays, S,
+                 slots.totals[0], ticket, colors, disparity, depth, kept, w_slots, stream())
+        res = ForwardRenderResult(colors, slots.first_oct_dis, disparity, depth, kept, w_slots, S, self, (lane, stamps[lane]))
+        res._keep = (slots, table16, fparams16, sparams16, bg, ticket)          # alive until the result dies (stream-ordered reuse)
+        return res
 
     def prefetch_next(self, rays_o, rays_d):
         """Software-pipeline the NEXT batch's ray march behind this batch's loss + backward.  Call right after ``Render``
@@ -456,17 +533,18 @@ class _RenderFunction(torch.autograd.Function):
         if _lib.lib.f2b_get_mlp_impl() == 1 and field.mlp_.n_hidden_matmuls == 0 and shader.mlp_.n_hidden_matmuls == 1:
             # fused epilogues (tcgen05 kernels): field MLP -> [logit | shader-MLP input row], shader MLP -> [raw | rgb];
             # the fp32 scene_feat of the ray samples is never materialised (edge points still need all 16 channels)
-            f_hidden = torch.empty((1, n_q, 64), dtype=torch.float16, device=dev) if grad_on else None
+            save = grad_on and not MLP_RECOMPUTE
+            f_hidden = torch.empty((1, n_q, 64), dtype=torch.float16, device=dev) if save else None
             logit = torch.empty((n_kept,), dtype=torch.float32, device=dev)
             mlp_in = torch.empty((n_kept, 32), dtype=torch.float16, device=dev)
             call("f2b_field_shade_fwd", feat16, fparams16, es.dirs, emb, pt_emb_idx, n_kept, logit, mlp_in, f_hidden, stream())
             if n_q > n_kept:
                 edge32 = torch.empty((n_q - n_kept, 16), dtype=torch.float32, device=dev)
                 call("f2b_mlp_fwd_f32", feat16[n_kept:], fparams16, 0, n_q - n_kept, edge32, None,
-                     f_hidden[0, n_kept:] if grad_on else None, stream())
+                     f_hidden[0, n_kept:] if save else None, stream())
             else:
                 edge32 = torch.empty((0, 16), dtype=torch.float32, device=dev)
-            s_hidden = torch.empty((2, n_kept, 64), dtype=torch.float16, device=dev) if grad_on else None
+            s_hidden = torch.empty((2, n_kept, 64), dtype=torch.float16, device=dev) if save else None
             raw = torch.empty((n_kept, 16), dtype=torch.float16, device=dev)
             rgb = torch.empty((n_kept, 3), dtype=torch.float32, device=dev)
             call("f2b_shader_mlp_rgb_fwd", mlp_in, sparams16, n_kept, raw, rgb, s_hidden, stream())
@@ -486,6 +564,7 @@ class _RenderFunction(torch.autograd.Function):
         ctx.pack = (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw,
                     s_hidden, rgb)
         ctx.gs_progress = renderer.global_data_pool_.gradient_scaling_progress_
+        ctx.grad_on = grad_on
         return colors, disparity, depth, weights, edge_feats
 
     @staticmethod
@@ -497,7 +576,7 @@ class _RenderFunction(torch.autograd.Function):
                                "(like tiny-cuda-nn's context, TCNNWP.cpp:207, the graph can be traversed once)")
         (fparams16, sparams16, q_pts, q_anchors, ray_emb_idx, bg, scene_feat, feat16, f_hidden, mlp_in, raw, s_hidden,
          rgb) = ctx.pack
-        if f_hidden is None:
+        if not ctx.grad_on:
             raise RuntimeError("Renderer.Render backward: forward ran without grad (VALIDATE mode / no_grad)")
         segments = q_pts
         n_q, dev = feat16.shape[0], feat16.device
@@ -558,17 +637,20 @@ class _RenderFunction(torch.autograd.Function):
             call("f2b_composite_act_bwd", scene_feat[0], int(scene_feat[1]), rgb, es.dt, es.t, bounds[r0:r1], bg[r0:r1], nr,
                  d_colors[r0:r1], None if d_disp is None else d_disp[r0:r1], None if d_depth is None else d_depth[r0:r1],
                  d_weights, float(ctx.gs_progress), raw, float(s_scale), d_logit, 1, d_raw, stream())
-            call("f2b_mlp_bwd2", d_raw[s0:s1], mlp_in[s0:s1], s_hidden[0, s0:s1], s_hidden[1, s0:s1] if nh_s else None,
-                 sparams16, int(nh_s), ns, d_in16[s0:s1], d_sparams, stream())
+            call("f2b_mlp_bwd2", d_raw[s0:s1], mlp_in[s0:s1], None if s_hidden is None else s_hidden[0, s0:s1],
+                 s_hidden[1, s0:s1] if (nh_s and s_hidden is not None) else None, sparams16, int(nh_s), ns, d_in16[s0:s1], d_sparams,
+                 stream())
             ops.shader_prep_bwd_f16(d_in16, d_logit, bounds[r0:r1], None if ray_emb_idx is None else ray_emb_idx[r0:r1],
                                     1.0 / s_scale, f_scale, d_scene16, d_app)
-            call("f2b_mlp_bwd2", d_scene16[s0:s1], feat16[s0:s1], f_hidden[0, s0:s1], f_hidden[1, s0:s1] if nh_f else None,
-                 fparams16, int(nh_f), ns, dfeat16[s0:s1], d_fparams, stream())
+            call("f2b_mlp_bwd2", d_scene16[s0:s1], feat16[s0:s1], None if f_hidden is None else f_hidden[0, s0:s1],
+                 f_hidden[1, s0:s1] if (nh_f and f_hidden is not None) else None, fparams16, int(nh_f), ns, dfeat16[s0:s1], d_fparams,
+                 stream())
             scatter(segments[0][0][s0:s1], segments[0][1][s0:s1], segments[0][2], s0, s1)
         for pts_e, anc_e, stride_e, first, rows in segments[1:]:          # TV-loss edge points: field MLP + scatter only
             if rows > 0:
-                call("f2b_mlp_bwd2", d_scene16[first:first + rows], feat16[first:first + rows], f_hidden[0, first:first + rows],
-                     f_hidden[1, first:first + rows] if nh_f else None, fparams16, int(nh_f), rows,
+                call("f2b_mlp_bwd2", d_scene16[first:first + rows], feat16[first:first + rows],
+                     None if f_hidden is None else f_hidden[0, first:first + rows],
+                     f_hidden[1, first:first + rows] if (nh_f and f_hidden is not None) else None, fparams16, int(nh_f), rows,
                      dfeat16[first:first + rows], d_fparams, stream())
                 scatter(pts_e, anc_e, stride_e, first, first + rows)
         if slab_hook is not None:

@@ -134,13 +134,17 @@ class PersSampler:
         return self.materialize(slots)
 
     # ---- slot-layout pieces (used by Renderer.Render; GetSamples = begin_march + march_rays + materialize) ----------
-    def begin_march(self, rays_o_raw, rays_d_raw, rays_noise=None, normalised=False):
-        """Normalise directions, draw the noise (PersSampler.cu:373-380) and bind the scratch; launches no march yet."""
+    def begin_march(self, rays_o_raw, rays_d_raw, rays_noise=None, normalised=False, lane=0):
+        """Normalise directions, draw the noise (PersSampler.cu:373-380) and bind the scratch; launches no march yet.
+        ``lane`` > 0 selects an additional scratch set (whole-image rendering keeps two chunks in flight on two streams);
+        lane 0 is the training scratch whose results die with the next lane-0 march."""
         rays_o = rays_o_raw.contiguous()
         rays_d = rays_d_raw if normalised else (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
         n_rays = rays_o.shape[0]
         if rays_noise is None:
             rays_noise = self.make_noise(n_rays, rays_o.device)
+        if lane:
+            return SlotSamples(self, rays_o, rays_d, rays_noise, self._scratch(n_rays, rays_o.device, lane), -int(lane))
         self._generation = getattr(self, "_generation", 0) + 1
         return SlotSamples(self, rays_o, rays_d, rays_noise, self._scratch(n_rays, rays_o.device), self._generation)
 
@@ -218,7 +222,7 @@ class PersSampler:
 
     def materialize(self, slots):
         """Slot layout -> the reference's SampleResultFlex (cumsum bounds, gathered arrays).  One host sync."""
-        if slots.generation != getattr(self, "_generation", 0):
+        if slots.generation >= 0 and slots.generation != getattr(self, "_generation", 0):
             raise RuntimeError("SampleResult: the sampler has marched again; this result's scratch slots were overwritten")
         R, dev = slots.n_rays, slots.rays_o.device
         bounds = torch.empty((R, 2), dtype=torch.int32, device=dev)
@@ -233,11 +237,17 @@ class PersSampler:
                                                        (slots.s_pts, slots.s_dt, slots.s_t, slots.s_anchors))
         return SampleResultFlex(pts, dirs, dt, t, anchors, bounds, slots.first_oct_dis)
 
-    def _scratch(self, n_rays, dev):
+    def _scratch(self, n_rays, dev, lane=0):
         """Persistent one-pass march scratch: a 1024-sample slot per ray (28 B/sample), grown on demand."""
         cap = max(n_rays, 1) * MAX_SAMPLE_PER_RAY
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        if lane:
+            pool = self.__dict__.setdefault("_scratch_lanes", {})
+            b = pool.get(lane)
+            if b is None or b[1].numel() < cap or b[0].device != dev:
+                b = pool[lane] = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
+            return b
         if getattr(self, "_scratch_cap", 0) < cap or self._scratch_bufs[0].device != dev:
-            f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
             self._scratch_bufs = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
             self._scratch_cap = cap
         return self._scratch_bufs

@@ -184,7 +184,10 @@ int f2b_field_shade_fwd(const void* feat_f16 /* [P,32] */, const void* field_par
 int f2b_shader_mlp_rgb_fwd(const void* mlp_in_f16, const void* shader_params_f16, int n_pts, void* raw_f16, float* rgb,
                            void* hidden_save_f16 /* [2,P,64] or NULL */, void* stream);
 /* f2b_mlp_bwd on a row range of a larger saved batch: the two activation layers are passed as separate pointers
- * (hidden1 NULL when n_hidden_matmuls == 0).  dparams is accumulated into, like f2b_mlp_bwd. */
+ * (hidden1 NULL when n_hidden_matmuls == 0).  dparams is accumulated into, like f2b_mlp_bwd.
+ * hidden0 == NULL (tcgen05 implementation only): the forward saved nothing — the kernel rebuilds the tile's hidden
+ * activations from in_f16 on the tensor pipe (bit-identical to what the forward would have saved) before the backward;
+ * 96 B read + 64 B written per sample instead of 224 / 352 + 64 (and the forward does not write 128 / 256 B). */
 int f2b_mlp_bwd2(const void* dout_f16, const void* in_f16, const void* hidden0_f16, const void* hidden1_f16,
                  const void* params_f16, int n_hidden_matmuls, int n_pts, void* din_f16, float* dparams_f32, void* stream);
 
@@ -396,6 +399,26 @@ int f2b_render_phase1(const f2b_render* r);
 int f2b_render_phase2_fwd(const f2b_render* r);
 int f2b_render_bwd(const f2b_render* r);
 int f2b_render_grad_finalize(const f2b_render* r);
+
+/* ---- forward-only (VALIDATE / no-grad) Renderer::Render behind the march as ONE kernel --------------------------------
+ * Replaces Renderer.cpp:107-208 for a batch that takes no gradient (ExpRunner::RenderWholeImage, ExpRunner.cpp:257-293):
+ * hash encode -> field MLP -> early stop (T > 1e-4, Renderer.cpp:125) -> shading-feature assembly + SH4 -> shader MLP ->
+ * colour activation -> composite, one CTA walking one ray front to back over the march's slot layout
+ * (slot_pts [R*slot,3], slot_dt / slot_t [R*slot], slot_anchors [R*slot,2], ray_counts [R] as f2b_sampler_march leaves them)
+ * and stopping at the first opaque sample — the samples behind it are never encoded.  No app embedding (Renderer.cpp:184
+ * applies it in TRAIN mode only).  rays_d normalised, bg [R,3].  total_all: device int, the batch's sample total (NULL or
+ * > 0: normal; <= 0: the reference's empty-batch result, depth = 512, Renderer.cpp:83-97).  ticket: [1] device int scratch.
+ * Outputs: colors [R,3], disparity [R], depth [R], kept_counts [R] (survivors per ray), and — nullable — weights_slots
+ * [R*slot]: the kept samples' weights at their slots (f2b_gather_kept_weights packs them into RenderResult.weights order).
+ * Values are bit-identical to f2b_render_phase1 + f2b_render_phase2_fwd on the same batch.  tcgen05 implementation only. */
+int f2b_render_fwd_fused(const void* table_f16, const int* prim_pool, const float* bias_pool, int n_volumes, int local_size,
+                         const void* field_params_f16, const void* shader_params_f16, const float* slot_pts, const float* slot_dt,
+                         const float* slot_t, const int* slot_anchors, const int* ray_counts, const float* rays_d, const float* bg,
+                         int n_rays, int slot_size, const int* total_all, int* ticket, float* colors, float* disparity,
+                         float* depth, int* kept_counts, float* weights_slots, void* stream);
+/* weights_slots [R*slot] + new_bounds [R,2] (f2b_count_scan of kept_counts) -> weights [P'] in the packed ray order. */
+int f2b_gather_kept_weights(const float* weights_slots, const int* new_bounds, int n_rays, int slot_size, float* weights,
+                            void* stream);
 
 #ifdef __cplusplus
 }

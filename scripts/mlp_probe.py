@@ -42,6 +42,8 @@ def main():
         din = torch.empty((n, 32), dtype=torch.float16, device=dev)
         dp = torch.zeros(p.numel(), device=dev)
         out[f"bwd_nh{nh}_ms"] = timed(lambda: call("f2b_mlp_bwd2", dout, x, hid[0], hid[nh] if nh else None, p, nh, n, din, dp, stream()))
+        out[f"bwd_nh{nh}_recompute_ms"] = timed(lambda: call("f2b_mlp_bwd2", dout, x, None, None, p, nh, n, din, dp, stream()))
+        out[f"bwd_nh{nh}_recompute_GBs"] = n * (32 + 64 + 64) / out[f"bwd_nh{nh}_recompute_ms"] / 1e6
         bytes_fwd_save = n * (64 + 32 + 128 * (nh + 1))
         out[f"fwd_nh{nh}_save_GBs"] = bytes_fwd_save / out[f"fwd_nh{nh}_save_ms"] / 1e6
         out[f"fwd_nh{nh}_nosave_GBs"] = n * 96 / out[f"fwd_nh{nh}_nosave_ms"] / 1e6

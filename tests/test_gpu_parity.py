@@ -225,6 +225,29 @@ def test_mlp_tc_tiles_and_f32_output(oracle, nh):
         assert_close(N(dp), N(dp0), rtol=3e-3, atol_frac=2e-3, name=f"dparams n={n}")
 
 
+@pytest.mark.parametrize("nh", [0, 1])
+def test_mlp_bwd_recompute_equals_saved(oracle, nh):
+    """f2b_mlp_bwd2 with hidden0 == NULL rebuilds the hidden activations on the tensor pipe from the input rows (no 128 / 256 B
+    per sample saved by the forward): dL/dinput must equal the saved-activation kernel's BIT FOR BIT (same UMMAs on the same
+    operands), the weight gradients up to the order of the fp32 atomics that flush them."""
+    from f2nerf_b200 import ops
+    from f2nerf_b200._lib import call, stream
+    rng = np.random.default_rng(310 + nh)
+    params = T((oracle.mlp_init(32, nh) * 2).astype(np.float16))
+    for n in (1, 127, 128, 129, 5000, 148 * 4 * 128 * 2 + 77):
+        x = T((rng.standard_normal((n, 32)) * 0.5).astype(np.float16))
+        dout = T((rng.standard_normal((n, 16)) * 0.1).astype(np.float16))
+        _, hid = ops.mlp_fwd(x, params, nh, save_hidden=True, impl="tc")
+        outs = []
+        for h0, h1 in ((hid[0], hid[1] if nh else None), (None, None)):
+            din = torch.empty((n, 32), dtype=torch.float16, device="cuda")
+            dp = torch.zeros(params.numel(), dtype=torch.float32, device="cuda")
+            call("f2b_mlp_bwd2", dout, x, h0, h1, params, nh, n, din, dp, stream())
+            outs.append((N(din), N(dp)))
+        np.testing.assert_array_equal(outs[0][0].view(np.uint16), outs[1][0].view(np.uint16))
+        assert_close(outs[1][1], outs[0][1], rtol=1e-5, atol_frac=1e-6, name=f"dparams recompute n={n}")
+
+
 def test_fused_epilogues_match_operator_sequence(oracle):
     """f2b_field_shade_fwd == mlp_fwd -> cast -> shader_prep and f2b_shader_mlp_rgb_fwd == mlp_fwd -> shader_act, bit for bit
     (ragged sizes, with and without appearance embedding, across several tiles per CTA)."""

@@ -213,6 +213,38 @@ def test_prefetched_march_equals_unpipelined(scene, gs_progress):
             np.testing.assert_array_equal(a, b, err_msg=str(k))
 
 
+@pytest.mark.parametrize("config", ["wanjinyou", "free"])
+def test_fused_forward_matches_operator_pipeline(config, monkeypatch):
+    """VALIDATE-mode Render through the ONE fused kernel behind the march (f2b_render_fwd_fused: encode -> field MLP -> early stop
+    -> SH + shader MLP -> composite per ray, stopping at the first opaque sample) against the operator pipeline
+    (f2b_render_phase1 + _phase2_fwd: every sample encoded, compaction, two MLP kernels, composite kernel) on the reference's
+    ngp_fox scene: every RenderResult field bit for bit — colours, depth, disparity, the packed weights and their bounds."""
+    import bench
+    from types import SimpleNamespace
+    from f2nerf_b200 import VALIDATE
+    prob = bench.build_problem(0, 1, SimpleNamespace(config=config, rays=1500), torch.device("cuda", 0))
+    renderer, gdp = prob["renderer"], prob["gdp"]
+    o, d, cam, _ = prob["host"]
+    o, d = o.copy(), d.copy()
+    o[7] = 600.; d[7] = 1.                                           # a ray that hits nothing
+    gdp.mode_ = VALIDATE
+    with torch.no_grad():
+        fused = renderer.Render(T(o), T(d), None, None)
+        assert type(fused).__name__ == "ForwardRenderResult"
+        f = {k: N(getattr(fused, k)) for k in ("colors", "disparity", "depth", "first_oct_dis", "weights", "idx_start_end")}
+        monkeypatch.setenv("F2B_FUSED_FORWARD", "0")
+        ref = renderer.Render(T(o), T(d), None, None)
+        assert type(ref).__name__ == "RenderResult"
+    kept = f["idx_start_end"][:, 1] - f["idx_start_end"][:, 0]
+    marched = N(renderer.sample_result_.pts_idx_bounds)
+    marched = marched[:, 1] - marched[:, 0]
+    assert (kept < marched).sum() > 100 and kept[7] == 0             # early termination is exercised
+    for k in f:
+        np.testing.assert_array_equal(f[k].view(np.uint32) if f[k].dtype == np.float32 else f[k],
+                                      N(getattr(ref, k)).view(np.uint32) if f[k].dtype == np.float32 else N(getattr(ref, k)), err_msg=k)
+    assert (f["colors"][7] == 0.5).all()
+
+
 def test_render_whole_image_matches_oracle(oracle):
     """N4: RenderWholeImage on rays of a reference ngp_fox camera (the committed fixture's blobs / cameras, the reference's
     parameter state) against the ORACLE's VALIDATE-mode forward of the same rays (noise == 1, background 0.5): sampler integers
