@@ -196,6 +196,34 @@ def ncu_traffic(name):
         return None
 
 
+def governing_roofline(name, per_launch_ms):
+    """The hardware rate that actually bounds the two table kernels, next to the HBM figure the contract asks for: both keep the
+    table L2-resident (17 MB live at log2 19), so DRAM bytes say little.  `units` per launch come from the committed ncu capture of
+    this same command (profiles/*_traffic.json: reduction / load sectors leaving the SM; deterministic for a seeded batch), the time
+    is THIS run's, the peak is the microbenchmark of the same instruction mix on this GPU type (scripts/microbench_red.cu /
+    microbench_gather.cu -> profiles/*_red_rate.json / *_gather_rate.json, random addresses in a table-sized L2-resident buffer)."""
+    import glob
+    spec = {"f2b_hash_bwd": ("l2_reduction_issue", "red_sectors_per_launch", "*_red_rate.json", "G lane-reductions/s"),
+            "f2b_field_fwd_slots": ("l1_l2_gather_sectors", "ld_sectors_per_launch", "*_gather_rate.json", "G 32B-sectors/s"),
+            "f2b_field_fwd": ("l1_l2_gather_sectors", "ld_sectors_per_launch", "*_gather_rate.json", "G 32B-sectors/s")}.get(name)
+    tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if spec is None or not tf or name not in NCU_KERNEL:
+        return None
+    try:
+        k = json.load(open(tf[-1]))["kernels"][NCU_KERNEL[name]]
+        units = float(k[spec[1]])
+        mb = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", spec[2])))[-1]))
+        if spec[0] == "l2_reduction_issue":
+            peak = max(r["g_lane_red_per_s"] for r in mb["rows"] if r["kind"] == "v2f32" and r["pattern"] == "spread")
+        else:
+            peak = max(r["spread_g_lane_gathers_per_s"] for r in mb["rows"] if r["table_mb"] <= 34)
+        ach = units / (per_launch_ms * 1e-3) / 1e9
+        return {"bound": spec[0], "achieved": ach, "peak": peak, "unit": spec[3], "frac": ach / peak, "units_per_launch": units,
+                "units_source": os.path.basename(tf[-1]), "peak_source": "microbenchmark, profiles/" + spec[2].replace("*", "rNN")}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def unit_count(name, ints):
     """number of samples (units) a traced call processed, from its integer arguments."""
     pos = {"f2b_field_fwd": 3, "f2b_hash_fwd": 3, "f2b_hash_bwd": 3, "f2b_mlp_fwd": 1, "f2b_mlp_bwd": 1, "f2b_shader_prep": 0,
@@ -292,25 +320,38 @@ def run_ours(args):
     trace, _lib.TRACE = _lib.TRACE, None
     # ---- end-to-end timing: pinned host rays -> device, loss -> host, every step ----------------
     barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     up = lambda: (h_o.to(device, non_blocking=True), h_d.to(device, non_blocking=True))
     prob["renderer"].pts_sampler_.take_prefetched(d_o, d_d)       # drop the resident loop's pending prefetch
     ro, rd = up()                                                 # pipeline fill (outside the timed region, like the warm-up)
-    barrier()
-    e2.record()
-    for _ in range(args.steps):                                   # per step: ONE upload of a ray batch (the next step's when the march
-        rc, rg = h_cam.to(device, non_blocking=True), h_gt.to(device, non_blocking=True)   # is pipelined), cam + gt of this step
-        if args.pipeline_march:
-            box = []
-            loss, res = train_step(prob, ro, rd, rc, rg, dist_sync, lambda: box.append(up()) or box[0])
-            ro, rd = box[0]
-        else:
-            loss, res = train_step(prob, ro, rd, rc, rg, dist_sync)
-            ro, rd = up()
-        loss_host = float(loss.item())
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    def e2e_loop(ro, rd):
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        w = []
+        for _ in range(args.steps):                               # per step: ONE upload of a ray batch (the next step's when the march
+            w0 = time.perf_counter()                              # is pipelined), cam + gt of this step, the loss back to the host
+            rc, rg = h_cam.to(device, non_blocking=True), h_gt.to(device, non_blocking=True)
+            if args.pipeline_march:
+                box = []
+                loss, res = train_step(prob, ro, rd, rc, rg, dist_sync, lambda: box.append(up()) or box[0])
+                ro, rd = box[0]
+            else:
+                loss, res = train_step(prob, ro, rd, rc, rg, dist_sync)
+                ro, rd = up()
+            loss_host = float(loss.item())
+            w.append(round((time.perf_counter() - w0) * 1e3, 2))
+        e3.record()
+        barrier()
+        return e2.elapsed_time(e3), w, ro, rd
+
+    e2e_attempts = []
+    for _ in range(2):                                            # same host-stall rule as the resident loop: reject + re-time ONCE
+        ms_e2e, e2e_walls, ro, rd = e2e_loop(ro, rd)
+        med = sorted(e2e_walls)[len(e2e_walls) // 2]
+        outlier = max(e2e_walls[1:] or e2e_walls) > 1.5 * med and max(e2e_walls[1:] or e2e_walls) - med > 2.5
+        e2e_attempts.append({"ms_per_step": ms_e2e / args.steps, "host_wall_ms_per_step": e2e_walls, "rejected": bool(outlier)})
+        if not outlier or world > 1:
+            break
     clocks.stop_flag = True
     clocks.join(timeout=2)
     if world > 1:
@@ -328,7 +369,10 @@ def run_ours(args):
         rec["ms"] += a.elapsed_time(b); rec["calls"] += 1; rec["units"] += (u or 0)
     peaks = load_peaks()
     total_traced = sum(v["ms"] for v in agg.values())
-    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    # dominant kernel ON THE STEP'S CRITICAL PATH: with the march software-pipelined it runs for the NEXT batch on a side stream
+    # behind this step's backward (Renderer.prefetch_next); it is listed in `rooflines` below but it is not what the step waits for
+    hidden = {"f2b_sampler_march"} if args.pipeline_march else set()
+    top = max(((k, v) for k, v in agg.items() if k not in hidden), key=lambda kv: kv[1]["ms"])
     name, rec = top
     per_launch_ms = rec["ms"] / rec["calls"]
     if name in ("f2b_mlp_fwd", "f2b_mlp_bwd"):
@@ -339,7 +383,17 @@ def run_ours(args):
         byts = ALGO_BYTES.get(name, 0) * units
         roof = dict(bound="hbm", achieved=byts / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=ncu_traffic(name), kernel=name, ms_per_launch=per_launch_ms,
-                share_of_step=rec["ms"] / max(total_traced, 1e-9), peak_source=peaks["src"])
+                share_of_step=rec["ms"] / max(total_traced, 1e-9), peak_source=peaks["src"],
+                governing=governing_roofline(name, rec["ms"] / args.steps))   # per STEP: the capture's units are the large launch
+                                                                               # (ray samples; the 16 k TV edge points add 0.5 %)
+    rooflines = []                                                  # the same two figures for the six largest kernels
+    for kname, krec in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:6]:
+        k_ms = krec["ms"] / krec["calls"]
+        k_units = krec["units"] / krec["calls"] if krec["units"] else n_samples / args.steps / max(world, 1)
+        hbm = ALGO_BYTES.get(kname, 0) * k_units / (k_ms * 1e-3) / 1e9 if kname in ALGO_BYTES else None
+        rooflines.append({"kernel": kname, "ms_per_launch": k_ms, "off_critical_path": kname in hidden,
+                          "hbm_frac_algorithmic": None if hbm is None else hbm / peaks["hbm"],
+                          "governing": governing_roofline(kname, krec["ms"] / args.steps)})
     rays_total = n_rays * world * args.steps
     cfg = prob["cfg"]
     line = {
@@ -352,11 +406,11 @@ def run_ours(args):
                               "mlp_impl": int(_lib.lib.f2b_get_mlp_impl())},
         "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in (h_o, h_d, h_cam, h_gt))) * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps, "timing_attempts": e2e_attempts},
         "gpu_launches": int(launches),
         "host_wall_ms_per_step": walls, "timing_attempts": attempts,
         "clocks": clocks.summary(),
-        "roofline": roof,
+        "roofline": roof, "rooflines": rooflines,
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in
                     sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -397,8 +451,23 @@ def forward_only_timing(prob, d_o, d_d, args, iters=20):
     finally:
         gdp.mode_ = TRAIN
     ms = e0.elapsed_time(e1) / iters
-    return {"value": prob["n_rays"] / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
-            "note": "the reference's number is reference_gpu.ms_validate_median on the same ray count"}
+    out = {"value": prob["n_rays"] / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "mode": "VALIDATE, no_grad",
+           "note": "the reference's number is reference_gpu.ms_validate_median on the same ray count"}
+    # the evaluation loop itself (ExpRunner::RenderWholeImage, ExpRunner.cpp:257-293): 8 x the batch as one "image", the
+    # reference's 8192-ray chunks, results to the host — chunks alternate between two streams (f2nerf_b200/eval.py)
+    from f2nerf_b200 import RenderWholeImage
+    big_o, big_d = d_o.repeat(8, 1), d_d.repeat(8, 1)
+    for _ in range(2):
+        RenderWholeImage(r, big_o, big_d)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        RenderWholeImage(r, big_o, big_d)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 5
+    out["whole_image"] = {"rays": int(big_o.shape[0]), "ms_per_image": wall * 1e3, "rays_per_s": big_o.shape[0] / wall,
+                          "note": "host wall time incl. the final device->host copy of the three images"}
+    return out
 
 
 def ray_generation_timing(prob, args, iters=20):

@@ -181,10 +181,11 @@ render_fwd_fused_kernel(const __half* __restrict__ table, const int* __restrict_
       }
       s_tau[tid] = tau;
       __syncthreads();
-      if (tid == 0) {
-        float a = run;
-        for (int j = 0; j < nv; j++) { s_acc[j] = a; a = fadd(a, s_tau[j]); }
-        s_acc[nv] = a;
+      if (tid == 0) {                                            // fixed trip count (lanes past nv hold tau = +0: x + 0 == x), so the
+        float a = run;                                           // loads pipeline ahead of the 128-long dependent add chain
+#pragma unroll 16
+        for (int j = 0; j < kRT; j++) { s_acc[j] = a; a = fadd(a, s_tau[j]); }
+        s_acc[kRT] = a;
         run = a;
       }
       __syncthreads();
@@ -229,9 +230,10 @@ render_fwd_fused_kernel(const __half* __restrict__ table, const int* __restrict_
         s_add[3 * 128 + tid] = fdiv(w, ts); s_add[4 * 128 + tid] = fmul(w, ts);
       }
       __syncthreads();
-      if (tid < 5) {                                             // FlexOps::Sum order: serial, left to right, kept samples only
-        const float* mine = s_add + tid * 128;
-        for (int j = 0; j < nk; j++) acc5 = fadd(acc5, mine[j]);
+      if (tid < 5) {                                             // FlexOps::Sum order: serial, left to right; samples that are not
+        const float* mine = s_add + tid * 128;                   // kept add +0 (w = 0), which leaves the running sum bit-identical
+#pragma unroll 16
+        for (int j = 0; j < kRT; j++) acc5 = fadd(acc5, mine[j]);
       }
       n_kept += nk;
       if (nk < nv) break;                                        // terminated inside this tile

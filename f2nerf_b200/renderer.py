@@ -44,10 +44,11 @@ class ForwardRenderResult:
     evaluation path (ExpRunner::RenderWholeImage, ExpRunner.cpp:257-293) reads them."""
     edge_feats = None
 
-    def __init__(self, colors, first_oct_dis, disparity, depth, kept_counts, w_slots, slot, owner, stamp):
+    def __init__(self, colors, first_oct_dis, disparity, depth, kept_counts, w_slots, slot, owner, stamp, total_all):
         self.colors, self.first_oct_dis, self.disparity, self.depth = colors, first_oct_dis, disparity, depth
         self.kept_counts = kept_counts
         self._w_slots, self._slot, self._owner, self._stamp, self._packed = w_slots, slot, owner, stamp, None
+        self._total_all = total_all                               # device [2]: samples / octree hits of the whole batch (march)
 
     def _pack(self):
         if self._packed is None:
@@ -55,8 +56,13 @@ class ForwardRenderResult:
                 raise RuntimeError("RenderResult.weights: a later Render re-used this result's slot-layout weights")
             n_rays, dev = self.kept_counts.shape[0], self.kept_counts.device
             bounds, total = ops.count_scan(self.kept_counts, n_rays)
-            w = torch.empty((int(total.item()),), dtype=torch.float32, device=dev)
-            call("f2b_gather_kept_weights", self._w_slots, bounds, n_rays, int(self._slot), w, stream())
+            n_kept, n_all = torch.cat([total, self._total_all[:1]]).tolist()
+            if n_all <= 0:                                        # the reference's empty-batch result leaves both undefined
+                self._packed = (None, None)                       # (Renderer.cpp:83-97)
+                return self._packed
+            w = torch.empty((int(n_kept),), dtype=torch.float32, device=dev)
+            if n_kept > 0:
+                call("f2b_gather_kept_weights", self._w_slots, bounds, n_rays, int(self._slot), w, stream())
             self._packed = (w, bounds)
         return self._packed
 
@@ -359,7 +365,8 @@ class Renderer:
             call("f2b_render_fwd_fused", table16, field.prim_pool_, field.bias_pool_, int(field.n_volumes_), int(field.local_size_),
                  fparams16, sparams16, slots.s_pts, slots.s_dt, slots.s_t, slots.s_anchors, slots.counts, slots.rays_d, bg, n_rays, S,
                  slots.totals[0], ticket, colors, disparity, depth, kept, w_slots, stream())
-        res = ForwardRenderResult(colors, slots.first_oct_dis, disparity, depth, kept, w_slots, S, self, (lane, stamps[lane]))
+        res = ForwardRenderResult(colors, slots.first_oct_dis, disparity, depth, kept, w_slots, S, self, (lane, stamps[lane]),
+                                  slots.totals[0])
         res._keep = (slots, table16, fparams16, sparams16, bg, ticket)          # alive until the result dies (stream-ordered reuse)
         return res
 

@@ -62,6 +62,16 @@ const auto kByte = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCU
 void* cur_stream() { return (void*) at::cuda::getCurrentCUDAStream().stream(); }
 void* P(const Tensor& t) { return t.defined() ? t.data_ptr() : nullptr; }
 // F2B_MLP_RECOMPUTE (default 1): the MLP forward saves no hidden activations, f2b_mlp_bwd2(hidden0 = NULL) rebuilds them
+// F2B_FUSED_FORWARD (default 1): VALIDATE-mode Render = march + f2b_render_fwd_fused; F2B_VALIDATE_WEIGHTS (default 1): also pack
+// RenderResult.weights / idx_start_end (costs the step's one host read)
+bool fused_forward() {
+  static const bool on = [] { const char* e = getenv("F2B_FUSED_FORWARD"); return !e || atoi(e) != 0; }();
+  return on;
+}
+bool validate_weights() {
+  static const bool on = [] { const char* e = getenv("F2B_VALIDATE_WEIGHTS"); return !e || atoi(e) != 0; }();
+  return on;
+}
 bool mlp_recompute() {
   static const bool on = [] { const char* e = getenv("F2B_MLP_RECOMPUTE"); return !e || atoi(e) != 0; }();
   return on;
@@ -289,6 +299,34 @@ RenderResult Renderer::Render(const Tensor& rays_o_raw, const Tensor& rays_d_raw
                               sampler->max_oct_intersect_per_ray_, /*count_all_hits=*/0, PF(w.s_pts), PF(w.s_dt), PF(w.s_t), PI(w.s_anchors),
                               PI(counts), PI(chunk_bounds), PI(heads) + 1, PF(first_oct_dis), cur_stream()));
   F2B_CHECK(f2b_slot_bounds(PI(counts), n_rays, kSlot, 0, PI(slot_bounds), cur_stream()));
+  if (!train && fused_forward()) {
+    // VALIDATE (ExpRunner::RenderWholeImage / TestImages under NoGradGuard): no gradient, no occupancy votes, no TV-loss edge points.
+    // Everything behind the march is ONE kernel walking each ray front to back — encode -> field MLP -> early stop -> SH + shader MLP
+    // -> composite — that stops at the first opaque sample (csrc/fused_fwd.cu); values bit-identical to the operator sequence below.
+    Tensor sparams16 = torch::empty({shader->mlp_->params_.numel()}, kHalf);
+    F2B_CHECK(f2b_cast_f32_to_f16(shader->mlp_->params_.data_ptr<float>(), P(sparams16), sparams16.numel(), 1.f, cur_stream()));
+    Tensor colors = torch::empty({n_rays, 3}, CUDAFloat), disp = torch::empty({n_rays}, CUDAFloat), depth = torch::empty({n_rays}, CUDAFloat);
+    Tensor kept = torch::empty({n_rays}, CUDAInt), ticket = torch::empty({1}, CUDAInt);
+    F2B_CHECK(f2b_render_fwd_fused(P(w.table16), field->prim_pool_.data_ptr<int>(), field->bias_pool_.data_ptr<float>(), field->n_volumes_,
+                                   local_size, P(fparams16), P(sparams16), PF(w.s_pts), PF(w.s_dt), PF(w.s_t), PI(w.s_anchors), PI(counts),
+                                   PF(rays_d), PF(bg), n_rays, kSlot, PI(heads) + 1, PI(ticket), PF(colors), PF(disp), PF(depth), PI(kept),
+                                   PF(w.w0), cur_stream()));
+    sample_result_ = SampleResultFlex();
+    sample_result_.first_oct_dis = first_oct_dis;
+    if (!validate_weights()) return {colors, first_oct_dis, disp, Tensor(), depth, Tensor(), Tensor()};
+    // RenderResult.weights / idx_start_end (Renderer.h:24-25) in the reference's packed ray order: one scan, the host read of the
+    // survivor total, one gather (nothing on the evaluation path reads them; F2B_VALIDATE_WEIGHTS=0 skips this and the sync)
+    Tensor new_bounds = torch::empty({n_rays, 2}, CUDAInt);
+    F2B_CHECK(f2b_count_scan(PI(kept), n_rays, PI(new_bounds), PI(heads), cur_stream()));
+    Tensor heads_cpu = heads.to(torch::kCPU);
+    const int64_t n_kept = heads_cpu[0].item<int>(), n_all = heads_cpu[1].item<int>();
+    sample_result_.pts = torch::empty({n_all, 0}, CUDAFloat);
+    if (n_all > 0) { burn_mlp_output(n_all); burn_mlp_output(n_kept); burn_mlp_output(n_kept); }   // the three TCNNWP::Query outputs (rng parity)
+    Tensor weights = torch::empty({n_kept}, CUDAFloat);
+    if (n_kept > 0) F2B_CHECK(f2b_gather_kept_weights(PF(w.w0), PI(new_bounds), n_rays, kSlot, PF(weights), cur_stream()));
+    if (n_all <= 0) return {bg, torch::zeros({n_rays, 1}, CUDAFloat), torch::zeros({n_rays}, CUDAFloat), Tensor(), torch::full({n_rays}, 512.f, CUDAFloat), Tensor(), Tensor()};
+    return {colors, first_oct_dis, disp, Tensor(), depth, weights, new_bounds};
+  }
   F2B_CHECK(f2b_field_fwd_slots(P(w.table16), field->prim_pool_.data_ptr<int>(), field->bias_pool_.data_ptr<float>(), field->n_volumes_,
                                 local_size, P(fparams16), PF(w.s_pts), PI(w.s_anchors), 2, PI(counts), n_rays, kSlot, 1, PF(w.logit_s),
                                 P(w.feat_s), cur_stream()));

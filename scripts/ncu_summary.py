@@ -23,6 +23,10 @@ COLS = [
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("lts__t_sectors_op_red.sum", "l2_red_sectors"),
+    ("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", "red_sectors"),      # lane-reductions leaving the SM (hash scatter)
+    ("smsp__inst_executed_op_global_red.sum", "red_insts"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "ld_sectors"),                # global-load sectors through L1 (hash gathers)
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "ld_requests"),
     ("lts__t_sectors_op_atom.sum", "l2_atom_sectors"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),

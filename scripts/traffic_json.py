@@ -23,9 +23,14 @@ def main():
         rec["launches"] += 1
         rec["dram_bytes_per_launch"] += float(r[col("dram_read")]) * scale[unit("dram_read")] + float(r[col("dram_write")]) * scale[unit("dram_write")]
         rec["ms_per_launch"] += float(r[col("time")]) * t_scale[unit("time")]
-    for rec in out.values():                       # same-named launches (ray samples / edge points): report the LARGEST-style mean
-        rec["dram_bytes_per_launch"] /= rec["launches"]
-        rec["ms_per_launch"] /= rec["launches"]
+        for key in ("red_sectors", "ld_sectors"):
+            try:
+                rec[key + "_per_launch"] = rec.get(key + "_per_launch", 0.0) + float(r[col(key)])
+            except StopIteration:
+                pass
+    for rec in out.values():                       # same-named launches (ray samples / edge points): mean over the launches
+        for k in [k for k in rec if k != "launches"]:
+            rec[k] /= rec["launches"]
     json.dump({"source": f"{src} (ncu --set full --clock-control none, bench.py --steps 1 --warmup 1)", "kernels": out}, open(dst, "w"), indent=1)
     print(f"{len(out)} kernels -> {dst}")
 
