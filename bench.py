@@ -153,10 +153,14 @@ def train_step(prob, rays_o, rays_d, emb_idx, gt, dist_sync=None, next_rays=None
     r = prob["renderer"]
     for p in (prob["field"].feat_pool_, prob["field"].mlp_.params_, prob["shader"].mlp_.params_, r.app_emb_):
         p.grad = None
-    res = r.Render(rays_o, rays_d, None, emb_idx)
+    nxt = None
     if next_rays is not None:
         nxt = next_rays() if callable(next_rays) else next_rays
-        r.prefetch_next(nxt[0], nxt[1])
+        if os.environ.get("F2B_EARLY_PREFETCH", "1") == "1":
+            r.set_next_rays(nxt[0], nxt[1])                        # Render launches their march itself, behind its occupancy votes
+    res = r.Render(rays_o, rays_d, None, emb_idx)
+    if nxt is not None:
+        r.prefetch_next(nxt[0], nxt[1])                            # no-op when Render already did
     color_loss = torch.sqrt((res.colors - gt) ** 2 + 1e-4).mean()
     var_loss = torch.sqrt(CustomOps.WeightVar(res.weights, res.idx_start_end) + 1e-2).mean()
     tv_loss = ((res.edge_feats[:, 0] - res.edge_feats[:, 1]) ** 2).mean()
@@ -425,6 +429,9 @@ def run_ours(args):
         ref_gpu = reference_gpu_timing(args)
         if ref_gpu is not None:
             line["reference_gpu"] = ref_gpu
+        cpp = cpp_host_timing(args)
+        if cpp is not None:
+            line["cpp_host"] = cpp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -550,6 +557,28 @@ def optimizer_timing(prob, iters=20):
     out.update(elements=int(p.numel()), live_elements=int(17 * field.local_size_),
                note="hash-table group only; ATen side includes the fp16 table copy of the next forward")
     return out
+
+
+def cpp_host_timing(args):
+    """Informational, N=1 only: the SAME harness (oracle/ref_driver.cpp: the reference's own program — Dataset, factories, autograd,
+    loss — 20 timed Render + loss.backward() on the seeded batch) with Renderer::Render replaced by the C++/LibTorch host of this
+    library (f2nerf_b200/shim/B200Renderer.cpp -> oracle/_ref/ref_driver_b200): the number a maintainer gets after the drop-in,
+    no Python anywhere."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver_b200")
+    cfg = W.CONFIGS[args.config]
+    if args.no_ref_gpu or int(os.environ.get("WORLD_SIZE", "1")) > 1 or cfg["ref_yaml"] is None or not os.path.exists(drv):
+        return None
+    try:
+        out_dir = "/tmp/f2b_cpp_bench"
+        r = subprocess.run([drv, os.path.join(ROOT, cfg["ref_yaml"]), out_dir, str(args.rays or cfg["rays"]), "20"],
+                           cwd=ROOT, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return {"unavailable": ("ref_driver_b200 rc %d: " % r.returncode) + r.stderr[-160:]}
+        t = json.load(open(os.path.join(out_dir, "ref_timing.json")))
+        t["note"] = "the reference's program with the B200 C++ host linked in as Renderer::Render (no march pipelining in this harness)"
+        return t
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
 
 
 def reference_gpu_timing(args):

@@ -301,9 +301,12 @@ class Renderer:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     sampler.update_oct_nodes_raw(slots.slot_bounds, slots.s_anchors, weights0, alphas0)
+                votes_done = torch.cuda.Event()
+                votes_done.record(side)                   # (the next batch's march may follow on the same stream)
                 gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
             n_pairs = N_EDGE_PTS if train else 0
             n_edge = 2 * n_pairs
+            early_prefetch = train and getattr(self, "next_rays_", None) is not None
             T = dict(pts=f32(n_kept, 3), dirs=f32(n_kept, 3), dt=f32(n_kept), t=f32(n_kept), anchors=i32(n_kept, 3),
                      feat_q=f16(n_kept + n_edge, 32), logit=f32(n_kept), mlp_in=f16(n_kept, 32), raw=f16(n_kept, 16),
                      rgb=f32(n_kept, 3), edge32=f32(n_edge, 16), colors=f32(n_rays, 3), disparity=f32(n_rays), depth=f32(n_rays),
@@ -316,6 +319,18 @@ class Renderer:
                 T.update(edge_idx=torch.randint(0, sampler.n_edges, (n_pairs,), dtype=torch.int32, device=dev),
                          edge_coord=torch.rand((n_pairs, 2), dtype=torch.float32, device=dev) * 2. - 1.,
                          e_pts=f32(n_edge, 3), e_anc=i32(n_edge))
+            if early_prefetch:
+                # Software-pipelined march of the NEXT batch (set_next_rays), issued NOW: right behind the occupancy votes on the
+                # side stream, into the other scratch set, while this batch still has its compaction / phase 2 / loss / backward
+                # ahead — it fills the host-bound gaps after the sync and is done before the dense backward starts.  Its noise is
+                # drawn at the Philox position the next Render will find: behind this Render's two remaining MLP-output draws
+                # and the coming backward's GradientScaling draws (rng.py).
+                mlp_out = lambda n: ((int(n) + 127) // 128 * 128) * 16 if n > 0 else 0
+                pending = [mlp_out(n_kept + n_edge), mlp_out(n_kept)]
+                if gdp.gradient_scaling_progress_ < 1. and n_kept > 0:
+                    pending += [n_kept * 3, n_kept]
+                nxt, self.next_rays_ = self.next_rays_, None
+                sampler.prefetch_march(nxt[0], nxt[1], side, pending)
             burn_mlp_output(n_kept + n_edge, dev)         # second AnchoredQuery (Renderer.cpp:165/172) ...
             burn_mlp_output(n_kept, dev)                  # ... and the shader MLP (SHShader.cpp:27)
             if train and self.use_app_emb_:
@@ -326,7 +341,7 @@ class Renderer:
         colors, disparity, depth, weights, edge_feats = _FusedRenderFunction.apply(
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, self, ra, keepalive, grad_on)
         if side is not None:
-            main.wait_stream(side)                                # joined before weights0 / alphas0 can be recycled
+            main.wait_event(votes_done)                           # votes joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, slots.first_oct_dis.clone(), disparity, edge_feats if train else None, depth, weights, new_bounds)
 
     def _fused_forward_ok(self, n_rays):
@@ -370,6 +385,12 @@ class Renderer:
         res._keep = (slots, table16, fparams16, sparams16, bg, ticket)          # alive until the result dies (stream-ordered reuse)
         return res
 
+    def set_next_rays(self, rays_o, rays_d):
+        """Hand over the ray tensors of the NEXT ``Render`` before calling this one (TRAIN mode): ``Render`` then launches their
+        march itself, right behind this batch's occupancy votes (earliest point at which the octree is final for it), instead of
+        the caller doing so afterwards through :meth:`prefetch_next`.  Results are bit-identical either way."""
+        self.next_rays_ = (rays_o, rays_d)
+
     def prefetch_next(self, rays_o, rays_d):
         """Software-pipeline the NEXT batch's ray march behind this batch's loss + backward.  Call right after ``Render``
         returned (TRAIN mode), with the ray tensors the next ``Render`` will be given: the march reads no trainable state, only
@@ -378,6 +399,10 @@ class Renderer:
         numbers, same octree state); a next ``Render`` with different rays simply ignores the prefetch."""
         gdp = self.global_data_pool_
         dev = rays_o.device
+        pf = getattr(self.pts_sampler_, "_prefetched", None)
+        if pf is not None and pf["key"][:3] == (rays_o.data_ptr(), rays_d.data_ptr(), rays_o.shape[0]):
+            return                                                  # Render already launched it (set_next_rays)
+        self.next_rays_ = None
         pending = ()
         if gdp.gradient_scaling_progress_ < 1. and getattr(self, "n_kept_pts_", 0) > 0:      # the coming backward's burns
             pending = (self.n_kept_pts_ * 3, self.n_kept_pts_)

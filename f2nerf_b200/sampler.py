@@ -189,8 +189,8 @@ class PersSampler:
         rays_d = (rays_d_raw / torch.linalg.norm(rays_d_raw, 2, -1, True)).contiguous()
         slots = self.begin_march(rays_o, rays_d, noise, normalised=True)
         ev = torch.cuda.Event()
-        ev.record(main)                                            # everything queued so far (compaction, votes' inputs) precedes the overwrite
-        stream.wait_event(ev)
+        ev.record(main)                                            # the ray upload / noise draw queued so far precede the march (the
+        stream.wait_event(ev)                                      # scratch it writes is the OTHER set: no reader to wait for)
         with torch.cuda.stream(stream):
             self.march_rays(slots, 0, n_rays)
             done = torch.cuda.Event()
@@ -210,6 +210,7 @@ class PersSampler:
         key = (rays_o_raw.data_ptr(), rays_d_raw.data_ptr(), rays_o_raw.shape[0], rays_o_raw._version, rays_d_raw._version)
         if (key != pf["key"] or pf["tree"] != self.tree_nodes_gpu_.data_ptr() or pf["mode"] != gdp.mode_
                 or pf["fineness"] != gdp.ray_march_fineness_ or pf["slots"].generation != getattr(self, "_generation", 0)):
+            # (a march in between took the other scratch set and bumped the generation: the prefetched slots are stale by order)
             torch.cuda.current_stream(rays_o_raw.device).wait_event(pf["done"])      # its buffers are released behind the march
             return None
         return pf
@@ -222,8 +223,8 @@ class PersSampler:
 
     def materialize(self, slots):
         """Slot layout -> the reference's SampleResultFlex (cumsum bounds, gathered arrays).  One host sync."""
-        if slots.generation >= 0 and slots.generation != getattr(self, "_generation", 0):
-            raise RuntimeError("SampleResult: the sampler has marched again; this result's scratch slots were overwritten")
+        if slots.generation >= 0 and slots.generation < getattr(self, "_generation", 0) - 1:
+            raise RuntimeError("SampleResult: the sampler has marched twice since; this result's scratch slots were overwritten")
         R, dev = slots.n_rays, slots.rays_o.device
         bounds = torch.empty((R, 2), dtype=torch.int32, device=dev)
         total = torch.zeros((1,), dtype=torch.int32, device=dev)
@@ -247,10 +248,14 @@ class PersSampler:
             if b is None or b[1].numel() < cap or b[0].device != dev:
                 b = pool[lane] = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
             return b
-        if getattr(self, "_scratch_cap", 0) < cap or self._scratch_bufs[0].device != dev:
-            self._scratch_bufs = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
-            self._scratch_cap = cap
-        return self._scratch_bufs
+        # two sets, used alternately: the march of batch i+1 can be issued while batch i's samples are still being read
+        # (Renderer.Render launches it right behind the occupancy votes, before the compaction of batch i has run)
+        sets = self.__dict__.setdefault("_scratch_sets", [None, None])
+        self._scratch_turn = 1 - getattr(self, "_scratch_turn", 1)
+        b = sets[self._scratch_turn]
+        if b is None or b[1].numel() < cap or b[0].device != dev:
+            b = sets[self._scratch_turn] = (f(cap, 3), f(cap), f(cap), torch.empty((cap, 2), dtype=torch.int32, device=dev))
+        return b
 
     def GetEdgeSamples(self, n_pts):
         """PersSampler::GetEdgeSamples (PersSampler.cu:454-473): (out_pts [n,2,3], out_idx [n,2])."""

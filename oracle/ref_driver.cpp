@@ -222,7 +222,7 @@ int main(int argc, char** argv) {
     loss.backward();
     dump("grad_field_mlp", field->mlp_->params_.grad());
     dump("grad_shader_mlp", shader->mlp_->params_.grad());
-    dump("grad_app_emb", renderer->app_emb_.grad());
+    if (renderer->app_emb_.grad().defined()) dump("grad_app_emb", renderer->app_emb_.grad());   // undefined when use_app_emb is false
     Tensor g = field->feat_pool_.grad().reshape({-1});
     if (full_grads) dump("grad_feat_pool", g);
     Tensor nz = torch::nonzero(g).reshape({-1});

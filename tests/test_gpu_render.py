@@ -184,8 +184,8 @@ def test_prefetched_march_equals_unpipelined(scene, gs_progress):
     from f2nerf_b200 import TRAIN
     batches = [make_rays(scene, n, seed=40 + i) for i, n in enumerate((150, 97, 150))]
     outs = []
-    for pipelined in (False, True):
-        gdp, sampler, field, shader, renderer = build(scene)
+    for pipelined in (False, True, "early"):               # "early": Render launches the next march itself (set_next_rays),
+        gdp, sampler, field, shader, renderer = build(scene)   # behind its occupancy votes, into the other scratch set
         gdp.mode_, gdp.gradient_scaling_progress_ = TRAIN, gs_progress
         torch.manual_seed(2024)
         dev_batches = [(T(o), T(d), T(cam)) for o, d, dn, cam in batches]
@@ -193,10 +193,15 @@ def test_prefetched_march_equals_unpipelined(scene, gs_progress):
         for i, (ro, rd, cam) in enumerate(dev_batches):
             for p in (field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, renderer.app_emb_):
                 p.grad = None
+            if pipelined == "early":
+                nxt = dev_batches[(i + 1) % len(dev_batches)]
+                renderer.set_next_rays(nxt[0], nxt[1])
             r = renderer.Render(ro, rd, None, cam)
-            if pipelined and i + 1 < len(dev_batches):
+            if pipelined == "early":
+                assert sampler._prefetched is not None             # launched inside Render
+            elif pipelined and i + 1 < len(dev_batches):
                 renderer.prefetch_next(dev_batches[i + 1][0], dev_batches[i + 1][1])
-            if pipelined and i + 1 == len(dev_batches):
+            elif pipelined and i + 1 == len(dev_batches):
                 renderer.prefetch_next(dev_batches[0][0], dev_batches[0][1])          # never consumed by a matching Render
             loss = (r.colors ** 2).mean() + r.disparity.mean() + 0.1 * ((r.edge_feats[:, 0] - r.edge_feats[:, 1]) ** 2).mean()
             loss.backward()
@@ -206,11 +211,12 @@ def test_prefetched_march_equals_unpipelined(scene, gs_progress):
         r = renderer.Render(dev_batches[1][0], dev_batches[1][1], None, dev_batches[1][2])
         rec += [N(r.colors), N(r.idx_start_end)]
         outs.append(rec)
-    for k, (a, b) in enumerate(zip(*outs)):
-        if a.dtype == np.float32 and k % 7 in (5, 6) and k < 21:      # atomically accumulated gradients: summation order only
-            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7 * np.abs(a).max())
-        else:
-            np.testing.assert_array_equal(a, b, err_msg=str(k))
+    for other in outs[1:]:
+        for k, (a, b) in enumerate(zip(outs[0], other)):
+            if a.dtype == np.float32 and k % 7 in (5, 6) and k < 21:      # atomically accumulated gradients: summation order only
+                np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7 * np.abs(a).max())
+            else:
+                np.testing.assert_array_equal(a, b, err_msg=str(k))
 
 
 @pytest.mark.parametrize("config", ["wanjinyou", "free"])
