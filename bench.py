@@ -200,6 +200,9 @@ def ncu_traffic(name):
         return None
 
 
+GOVERNING_OK = True      # main() clears it for any workload other than the one the committed ncu capture was taken on
+
+
 def governing_roofline(name, per_launch_ms):
     """The hardware rate that actually bounds the two table kernels, next to the HBM figure the contract asks for: both keep the
     table L2-resident (17 MB live at log2 19), so DRAM bytes say little.  `units` per launch come from the committed ncu capture of
@@ -211,7 +214,7 @@ def governing_roofline(name, per_launch_ms):
             "f2b_field_fwd_slots": ("l1_l2_gather_sectors", "ld_sectors_per_launch", "*_gather_rate.json", "G 32B-sectors/s"),
             "f2b_field_fwd": ("l1_l2_gather_sectors", "ld_sectors_per_launch", "*_gather_rate.json", "G 32B-sectors/s")}.get(name)
     tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
-    if spec is None or not tf or name not in NCU_KERNEL:
+    if spec is None or not tf or name not in NCU_KERNEL or not GOVERNING_OK:
         return None
     try:
         k = json.load(open(tf[-1]))["kernels"][NCU_KERNEL[name]]
@@ -252,6 +255,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
         from f2nerf_b200.dist import allreduce_step
         dist_sync = allreduce_step
+    global GOVERNING_OK
+    GOVERNING_OK = args.config == "wanjinyou" and not args.rays   # the sector counts in profiles/*_traffic.json are this batch's
     prob = build_problem(rank, world, args, device)
     n_rays = prob["n_rays"]                                     # rays THIS rank renders per step
     if world > 1:

@@ -157,9 +157,13 @@ hash_bwd_kernel(const int* __restrict__ prim_pool, const float* __restrict__ bia
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int lmask = (1 << log2_levels) - 1;
-  for (int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += stride)
-    hash_bwd_task<GRAD_F16>(w >> log2_levels, level_lo + int(w & lmask), lane, prim_pool, bias_pool, n_volumes, local_size, pts, vol,
-                            vol_stride, n_pts, grad_feat, grad_mul, grad_table);
+  // A warp would otherwise keep ONE level for all its tasks (the stride is a multiple of the level count) and the fine-level warps
+  // (8 reductions per lane, no merging) would finish long after the coarse-level ones: rotate the level by the iteration count —
+  // within every stride-sized block of tasks each (32 samples, level) pair is still visited exactly once.
+  int k = 0;
+  for (int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += stride, k++)
+    hash_bwd_task<GRAD_F16>(w >> log2_levels, level_lo + ((int(w & lmask) + k) & lmask), lane, prim_pool, bias_pool, n_volumes, local_size,
+                            pts, vol, vol_stride, n_pts, grad_feat, grad_mul, grad_table);
 }
 
 __global__ void level_scales_kernel(float* out) {
@@ -226,7 +230,10 @@ extern "C" int f2b_hash_bwd_levels(const int* prim_pool, const float* bias_pool,
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   const int64_t want = div_up(n_tasks * 32, int64_t(256));
-  const int blocks = int(want < int64_t(sms) * ctas_per_sm ? want : int64_t(sms) * ctas_per_sm);
+  int blocks = int(want < int64_t(sms) * ctas_per_sm ? want : int64_t(sms) * ctas_per_sm);
+  // persistent grid: the warp count (8 per block) must be a multiple of n_levels (<= 16) for the kernel's level rotation to visit
+  // every task exactly once
+  if (blocks < want && ((blocks * 8) % n_levels) != 0) blocks = blocks > 1 ? blocks - 1 : int(want);
   if (grad_is_f16)
     hash_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(prim_pool, bias_pool, n_volumes, local_size, pts, vol, vol_stride,
                                                                  n_pts, grad_feat, grad_mul, grad_table, n_tasks, level_lo, log2_levels);

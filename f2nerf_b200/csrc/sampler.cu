@@ -311,8 +311,12 @@ march_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ t
 constexpr int kL16 = 16;
 constexpr int kRaysPerBlock16 = 2;
 
-template <int MODE>
-__global__ void __launch_bounds__(32)
+// LEAN: the same kernel compiled for <= 64 registers (13 words of spill) for the software-pipelined march of the NEXT batch, which
+// shares the SMs with this batch's backward: at 96 registers its 14 resident one-warp CTAs per SM hold 43 k of the 64 k registers
+// and halve the occupancy of everything that runs beside it (r02d timeline: compaction 0.15 -> 0.35 ms, composite backward 0.14 ->
+// 0.33 ms); identical arithmetic, identical results.
+template <int MODE, bool LEAN = false>
+__global__ void __launch_bounds__(32, LEAN ? 32 : 1)
 march16_kernel(const TreeNode* __restrict__ nodes, const TransInfo* __restrict__ trans,
                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                const float* __restrict__ rays_noise, int n_rays, float near0, float far0,
@@ -618,6 +622,11 @@ static int march_lanes() {
     else march16_kernel<MODE><<<div_up(n_rays, kRaysPerBlock16), 32, 0, st>>>(__VA_ARGS__);               \
   } while (0)
 
+static int march_slots(bool lean, const void* tree_nodes, int n_nodes, const void* trans, int n_trans, const float* rays_o,
+                       const float* rays_d, const float* rays_noise, int n_rays, float near, float far, float sample_l,
+                       int scale_by_dis, int max_oct_intersect_per_ray, int count_all_hits, float* s_pts, float* s_dt, float* s_t,
+                       int* s_anchors, int* ray_counts, int* pts_idx_bounds, int* totals, float* first_oct_dis, void* stream);
+
 extern "C" int f2b_sampler_count(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
                                  const float* rays_o, const float* rays_d, const float* rays_noise,
                                  int n_rays, float near, float far, float sample_l, int scale_by_dis,
@@ -660,6 +669,27 @@ extern "C" int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void
                                  int max_oct_intersect_per_ray, int count_all_hits, float* s_pts, float* s_dt,
                                  float* s_t, int* s_anchors, int* ray_counts, int* pts_idx_bounds, int* totals,
                                  float* first_oct_dis, void* stream) {
+  return march_slots(false, tree_nodes, n_nodes, trans, n_trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l, scale_by_dis,
+                     max_oct_intersect_per_ray, count_all_hits, s_pts, s_dt, s_t, s_anchors, ray_counts, pts_idx_bounds, totals,
+                     first_oct_dis, stream);
+}
+
+// Same march, compiled to share the SMs (<= 64 registers): for a march that runs in the background of other kernels.
+extern "C" int f2b_sampler_march_bg(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                                    const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                                    float near, float far, float sample_l, int scale_by_dis,
+                                    int max_oct_intersect_per_ray, int count_all_hits, float* s_pts, float* s_dt,
+                                    float* s_t, int* s_anchors, int* ray_counts, int* pts_idx_bounds, int* totals,
+                                    float* first_oct_dis, void* stream) {
+  return march_slots(true, tree_nodes, n_nodes, trans, n_trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l, scale_by_dis,
+                     max_oct_intersect_per_ray, count_all_hits, s_pts, s_dt, s_t, s_anchors, ray_counts, pts_idx_bounds, totals,
+                     first_oct_dis, stream);
+}
+
+static int march_slots(bool lean, const void* tree_nodes, int n_nodes, const void* trans, int n_trans, const float* rays_o,
+                       const float* rays_d, const float* rays_noise, int n_rays, float near, float far, float sample_l,
+                       int scale_by_dis, int max_oct_intersect_per_ray, int count_all_hits, float* s_pts, float* s_dt, float* s_t,
+                       int* s_anchors, int* ray_counts, int* pts_idx_bounds, int* totals, float* first_oct_dis, void* stream) {
   F2B_REQUIRE(n_rays >= 0 && n_nodes > 0 && n_trans >= 0, "f2b_sampler_march: bad sizes");
   F2B_REQUIRE(totals, "f2b_sampler_march: null totals");
   cudaStream_t st = as_stream(stream);
@@ -667,10 +697,16 @@ extern "C" int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void
   if (n_rays == 0) return check_launch("f2b_sampler_march");
   F2B_REQUIRE(tree_nodes && trans && rays_o && rays_d && rays_noise && s_pts && s_dt && s_t && s_anchors && ray_counts &&
               pts_idx_bounds && first_oct_dis, "f2b_sampler_march: null pointer");
-  F2B_LAUNCH_MARCH(2, st,
-      (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l,
-      scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, s_pts, nullptr, s_dt, s_t,
-      s_anchors, first_oct_dis);
+  if (lean && march_lanes() == 16)
+    march16_kernel<2, true><<<div_up(n_rays, kRaysPerBlock16), 32, 0, st>>>(
+        (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l,
+        scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, s_pts, nullptr, s_dt, s_t,
+        s_anchors, first_oct_dis);
+  else
+    F2B_LAUNCH_MARCH(2, st,
+        (const TreeNode*)tree_nodes, (const TransInfo*)trans, rays_o, rays_d, rays_noise, n_rays, near, far, sample_l,
+        scale_by_dis, max_oct_intersect_per_ray, count_all_hits, ray_counts, totals + 1, nullptr, s_pts, nullptr, s_dt, s_t,
+        s_anchors, first_oct_dis);
   scan_counts_kernel<<<1, 1024, 0, st>>>(ray_counts, n_rays, pts_idx_bounds, totals);
   return check_launch("f2b_sampler_march");
 }

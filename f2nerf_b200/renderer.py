@@ -280,6 +280,53 @@ class Renderer:
             call("f2b_render_phase1", ra)
             if pf is not None:
                 _lib.LAUNCHES -= 3                                    # march (2 kernels) + slot bounds ran with the prefetch
+            n_pairs = N_EDGE_PTS if train else 0
+            n_edge = 2 * n_pairs
+            side = votes_done = None
+
+            def launch_votes():
+                # octree occupancy votes only feed the NEXT march: on the side stream, device-ordered behind phase 1 (no host value)
+                nonlocal side, votes_done
+                side = self._side_stream(dev, 1)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sampler.update_oct_nodes_raw(slots.slot_bounds, slots.s_anchors, weights0, alphas0)
+                votes_done = torch.cuda.Event()
+                votes_done.record(side)                               # (the next batch's march may follow on the same stream)
+
+            def phase2_buffers(rows):
+                """Buffers of the second half for up to ``rows`` surviving samples + the TV-loss edge draws (the reference's RNG
+                order: after the early-stop query's output draw, before the second query's)."""
+                T = dict(pts=f32(rows, 3), dirs=f32(rows, 3), dt=f32(rows), t=f32(rows), anchors=i32(rows, 3),
+                         feat_q=f16(rows + n_edge, 32), logit=f32(rows), mlp_in=f16(rows, 32), raw=f16(rows, 16),
+                         rgb=f32(rows, 3), edge32=f32(n_edge, 16), colors=f32(n_rays, 3), disparity=f32(n_rays), depth=f32(n_rays),
+                         weights=f32(rows))
+                if grad_on and not MLP_RECOMPUTE:
+                    T.update(f_hidden=f16(1, rows + n_edge, 64), s_hidden=f16(2, rows, 64))
+                if train:                                             # TV-loss edge points: the reference's draws
+                    if sampler.n_edges <= 0:
+                        raise RuntimeError("GetEdgeSamples: empty edge pool (needs >= 2 face-adjacent valid leaves)")
+                    T.update(edge_idx=torch.randint(0, sampler.n_edges, (n_pairs,), dtype=torch.int32, device=dev),
+                             edge_coord=torch.rand((n_pairs, 2), dtype=torch.float32, device=dev) * 2. - 1.,
+                             e_pts=f32(n_edge, 3), e_anc=i32(n_edge))
+                if train and self.use_app_emb_:
+                    T.update(ray_emb_idx=emb_idx.to(torch.int32).contiguous(), pt_emb_idx=i32(rows))
+                return T
+
+            # A prefetched march brought its sample total to the host long ago (pinned copy behind the march): everything that
+            # needs only that total — the early-stop query's RNG draw, the votes, the edge draws, the phase-2 buffers (sized for
+            # all marched samples, an upper bound of the survivors) — is issued NOW, while the GPU runs phase 1, instead of in
+            # the gap behind the sync.
+            pre_all = None
+            if pf is not None and pf.get("host_totals") is not None:
+                pf["done"].synchronize()                  # the march (and the pinned copy behind it) finished during the last backward
+                pre_all = int(pf["host_totals"][0])
+            T = None
+            if pre_all is not None and pre_all > 0 and os.environ.get("F2B_PRESYNC_HOST", "1") == "1":
+                burn_mlp_output(pre_all, dev)             # RNG parity: the reference's MLP output is a torch::rand (rng.py)
+                if train:
+                    launch_votes()
+                T = phase2_buffers(pre_all)
             n_kept, n_all, n_all_oct = heads.tolist()                 # THE host sync of the step
             self._bwd_cuts_ = None
             sampler.note_totals(n_rays, n_all_oct)
@@ -294,52 +341,32 @@ class Renderer:
                 z = torch.zeros
                 return RenderResult(bg, z((n_rays, 1), device=dev), z((n_rays,), device=dev), None,
                                     torch.full((n_rays,), 512., device=dev), None, None)
-            burn_mlp_output(n_all, dev)                   # RNG parity: the reference's MLP output is a torch::rand (rng.py)
-            side = None
+            if T is None:
+                burn_mlp_output(n_all, dev)               # RNG parity: the reference's MLP output is a torch::rand (rng.py)
+                if train:
+                    launch_votes()
+                T = phase2_buffers(n_kept)
+            elif pre_all != n_all:
+                raise RuntimeError(f"Renderer.Render: prefetched march total {pre_all} != {n_all}")
+            T["weights"] = T["weights"][:n_kept]          # the one per-sample tensor handed out (RenderResult.weights)
             if train:
-                side = self._side_stream(dev, 1)          # octree votes feed the NEXT march: beside the gradient pass
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    sampler.update_oct_nodes_raw(slots.slot_bounds, slots.s_anchors, weights0, alphas0)
-                votes_done = torch.cuda.Event()
-                votes_done.record(side)                   # (the next batch's march may follow on the same stream)
                 gdp.meaningful_sampled_pts_per_ray_ = gdp.meaningful_sampled_pts_per_ray_ * .9 + (n_kept / n_rays) * .1
-            n_pairs = N_EDGE_PTS if train else 0
-            n_edge = 2 * n_pairs
-            early_prefetch = train and getattr(self, "next_rays_", None) is not None
-            T = dict(pts=f32(n_kept, 3), dirs=f32(n_kept, 3), dt=f32(n_kept), t=f32(n_kept), anchors=i32(n_kept, 3),
-                     feat_q=f16(n_kept + n_edge, 32), logit=f32(n_kept), mlp_in=f16(n_kept, 32), raw=f16(n_kept, 16),
-                     rgb=f32(n_kept, 3), edge32=f32(n_edge, 16), colors=f32(n_rays, 3), disparity=f32(n_rays), depth=f32(n_rays),
-                     weights=f32(n_kept))
-            if grad_on and not MLP_RECOMPUTE:
-                T.update(f_hidden=f16(1, n_kept + n_edge, 64), s_hidden=f16(2, n_kept, 64))
-            if train:                                                                 # TV-loss edge points: the reference's draws
-                if sampler.n_edges <= 0:
-                    raise RuntimeError("GetEdgeSamples: empty edge pool (needs >= 2 face-adjacent valid leaves)")
-                T.update(edge_idx=torch.randint(0, sampler.n_edges, (n_pairs,), dtype=torch.int32, device=dev),
-                         edge_coord=torch.rand((n_pairs, 2), dtype=torch.float32, device=dev) * 2. - 1.,
-                         e_pts=f32(n_edge, 3), e_anc=i32(n_edge))
-            if early_prefetch:
-                # Software-pipelined march of the NEXT batch (set_next_rays), issued NOW: right behind the occupancy votes on the
-                # side stream, into the other scratch set, while this batch still has its compaction / phase 2 / loss / backward
-                # ahead — it fills the host-bound gaps after the sync and is done before the dense backward starts.  Its noise is
-                # drawn at the Philox position the next Render will find: behind this Render's two remaining MLP-output draws
-                # and the coming backward's GradientScaling draws (rng.py).
-                mlp_out = lambda n: ((int(n) + 127) // 128 * 128) * 16 if n > 0 else 0
-                pending = [mlp_out(n_kept + n_edge), mlp_out(n_kept)]
-                if gdp.gradient_scaling_progress_ < 1. and n_kept > 0:
-                    pending += [n_kept * 3, n_kept]
-                nxt, self.next_rays_ = self.next_rays_, None
-                sampler.prefetch_march(nxt[0], nxt[1], side, pending)
             burn_mlp_output(n_kept + n_edge, dev)         # second AnchoredQuery (Renderer.cpp:165/172) ...
             burn_mlp_output(n_kept, dev)                  # ... and the shader MLP (SHShader.cpp:27)
             if train and self.use_app_emb_:
-                T.update(ray_emb_idx=emb_idx.to(torch.int32).contiguous(), pt_emb_idx=i32(n_kept))
                 ra.set(app_emb=self.app_emb_.detach(), n_emb=self.app_emb_.shape[0])
             ra.set(n_kept=n_kept, n_edge_pairs=n_pairs, **T)
             keepalive = (slots, table16, fparams16, sparams16, new_bounds, heads, bg, T)
         colors, disparity, depth, weights, edge_feats = _FusedRenderFunction.apply(
             field.feat_pool_, field.mlp_.params_, shader.mlp_.params_, self.app_emb_, self, ra, keepalive, grad_on)
+        if train and getattr(self, "next_rays_", None) is not None:
+            # Software-pipelined march of the NEXT batch (set_next_rays): launched as soon as phase 2 is enqueued, behind the
+            # occupancy votes on the side stream, into the other march scratch set — it runs under this batch's phase 2 / loss /
+            # backward.  Its noise is drawn at the Philox position the next Render will find: behind the coming backward's
+            # GradientScaling draws (rng.py).
+            pending = [n_kept * 3, n_kept] if (gdp.gradient_scaling_progress_ < 1. and n_kept > 0) else []
+            nxt, self.next_rays_ = self.next_rays_, None
+            sampler.prefetch_march(nxt[0], nxt[1], side, pending)
         if side is not None:
             main.wait_event(votes_done)                           # votes joined before weights0 / alphas0 can be recycled
         return RenderResult(colors, slots.first_oct_dis.clone(), disparity, edge_feats if train else None, depth, weights, new_bounds)
@@ -407,6 +434,30 @@ class Renderer:
         if gdp.gradient_scaling_progress_ < 1. and getattr(self, "n_kept_pts_", 0) > 0:      # the coming backward's burns
             pending = (self.n_kept_pts_ * 3, self.n_kept_pts_)
         self.pts_sampler_.prefetch_march(rays_o, rays_d, self._side_stream(dev, 1), pending)
+
+    def _table_grad_buffer(self, shape, dev):
+        """The fp32 table gradient handed to autograd.  Only floats [0, 17*S) of it are ever written (the half-overlapping level
+        layout leaves the other 15/32 of the pool without gradient for ever), so the STORAGE is kept across steps and only that
+        live prefix is zero-filled per backward (34 of 64 MB at log2 19, 272 of 512 MB at log2 22) — as long as no tensor on last
+        step's gradient is alive any more (storage use count): a trainer that keeps ``.grad`` (zero_grad(set_to_none=False),
+        gradient accumulation) gets a fresh, fully zeroed tensor instead.  Every backward returns a NEW tensor object on the
+        storage, so autograd still takes it as ``.grad`` without a copy."""
+        self._table_grad_tail_zero = False
+        n = 1
+        for d in shape:
+            n *= int(d)
+        st = getattr(self, "_d_table_storage_", None)
+        try:
+            if st is not None and st.nbytes() == 4 * n and st.device == torch.device(dev) and torch._C._storage_Use_Count(st._cdata) == 1:
+                self._table_grad_tail_zero = True              # the dead tail has been zero since the storage was created
+                return torch.empty(0, dtype=torch.float32, device=dev).set_(st, 0, tuple(shape))
+            buf = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
+            self._d_table_storage_ = buf.untyped_storage()
+            self._table_grad_tail_zero = True                  # just zeroed as a whole
+            return buf
+        except (AttributeError, RuntimeError):                 # private use-count API missing: a plain per-step allocation, zeroed as a whole
+            self._d_table_storage_ = None
+            return torch.empty(tuple(shape), dtype=torch.float32, device=dev)
 
     def _side_stream(self, dev, i=1):
         pool = self.__dict__.setdefault("_streams_", {})
@@ -516,14 +567,16 @@ class _FusedRenderFunction(torch.autograd.Function):
         grad_mul = (1.0 / f_scale) * (getattr(renderer, "grad_premul_", 1.0) if slab_hook is not None else 1.0)
         B = dict(d_logit=f32(n_kept), d_raw=f16(n_kept, 16), d_in16=f16(n_kept, 32), d_scene16=f16(n_kept + n_edge, 16),
                  dfeat16=f16(n_kept + n_edge, 32), d_sparams=f32(ra.n_shader_params), d_fparams=f32(ra.n_field_params),
-                 d_table=torch.empty(ctx.table_shape, dtype=torch.float32, device=dev),
+                 d_table=renderer._table_grad_buffer(ctx.table_shape, dev),
                  nonfinite=torch.empty((2,), dtype=torch.int32, device=dev))
         if emb_on:
             B["d_app"] = torch.empty(ctx.emb_shape, dtype=torch.float32, device=dev)
         side = renderer._side_stream(dev, 2)
         ra.set(d_colors=d_colors, d_disparity=d_disp, d_depth=d_depth, d_weights=d_weights, d_edge=d_edge,
                gs_progress=float(ctx.gs_progress), shader_loss_scale=float(shader.mlp_.loss_scale_), field_loss_scale=float(f_scale),
-               table_grad_mul=float(grad_mul), table_numel=B["d_table"].numel(),
+               table_grad_mul=float(grad_mul),
+               # floats to zero-fill: the live prefix only when the buffer's dead tail is known to be zero already
+               table_numel=min(B["d_table"].numel(), 17 * int(field.local_size_)) if renderer._table_grad_tail_zero else B["d_table"].numel(),
                table_live=min(B["d_table"].numel(), 17 * int(field.local_size_)), scatter_mode=int(slab_hook is not None),
                stream=main.cuda_stream, side_stream=side.cuda_stream, **B)
         call("f2b_render_bwd", ra)

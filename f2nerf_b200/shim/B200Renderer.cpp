@@ -98,6 +98,7 @@ void burn_mlp_output(int64_t batch) { if (batch > 0) burn_rand(((batch + 127) / 
 struct Work {
   int64_t cap_rays = 0;
   Tensor s_pts, s_dt, s_t, s_anchors, logit_s, feat_s, w0, a0, keep, kept_counts, table16;
+  c10::Storage d_table_storage;          // the table gradient's storage, kept across steps (its dead 15/32 stays zero)
   c10::optional<c10::cuda::CUDAStream> side_votes, side_scatter;
   void ensure(int64_t n_rays, int64_t table_numel) {
     if (n_rays > cap_rays) {
@@ -211,9 +212,18 @@ public:
     const int64_t table_numel = ctx->saved_data["table_numel"].toInt();
     const int local_size = ((field->pool_size_ / N_LEVELS) >> 4) << 4;
     const int64_t live = std::min<int64_t>(table_numel, int64_t(N_LEVELS + 1) * local_size);     // halves [0, 17 S) are ever addressed
-    Tensor d_table = torch::empty({table_numel / 2, 2}, CUDAFloat);
-    d_table.view({-1}).slice(0, 0, live).zero_();
-    if (live < table_numel) d_table.view({-1}).slice(0, live, table_numel).zero_();
+    // Only floats [0, 17 S) of the gradient are ever written, so its storage is kept across steps and only that live prefix is
+    // zero-filled per backward — unless a tensor on last step's gradient is still alive (a trainer that keeps .grad): then a fresh,
+    // fully zeroed one.  Each backward hands autograd a NEW tensor on the storage, so it becomes .grad without a copy.
+    Work& wk = work_of(k.renderer);
+    Tensor d_table;
+    if (wk.d_table_storage && wk.d_table_storage.nbytes() == size_t(table_numel) * 4 && wk.d_table_storage.use_count() == 1) {
+      d_table = torch::empty({0}, CUDAFloat).set_(wk.d_table_storage, 0, {table_numel / 2, 2});
+      d_table.view({-1}).slice(0, 0, live).zero_();
+    } else {
+      d_table = torch::zeros({table_numel / 2, 2}, CUDAFloat);
+      wk.d_table_storage = d_table.storage();
+    }
     const bool emb_on = k.ray_emb_idx.defined();
     Tensor d_app = emb_on ? torch::zeros({ctx->saved_data["n_emb"].toInt(), 16}, CUDAFloat) : Tensor();
     if (n_q > n_kept) {

@@ -77,6 +77,16 @@ int f2b_sampler_march(const void* tree_nodes, int n_nodes, const void* trans, in
                       float* s_pts, float* s_dt, float* s_t, int* s_anchors,
                       int* ray_counts /* [n_rays] */, int* pts_idx_bounds /* [n_rays,2] out */, int* totals /* [2] out */,
                       float* first_oct_dis /* [n_rays] out */, void* stream);
+/* The same march compiled for <= 64 registers per thread (identical arithmetic and results): for the software-pipelined march of
+ * the NEXT batch, which runs on a side stream under this batch's backward and must leave the register file to the kernels it
+ * shares the SMs with. */
+int f2b_sampler_march_bg(const void* tree_nodes, int n_nodes, const void* trans, int n_trans,
+                      const float* rays_o, const float* rays_d, const float* rays_noise, int n_rays,
+                      float near, float far, float sample_l, int scale_by_dis,
+                      int max_oct_intersect_per_ray, int count_all_hits,
+                      float* s_pts, float* s_dt, float* s_t, int* s_anchors,
+                      int* ray_counts /* [n_rays] */, int* pts_idx_bounds /* [n_rays,2] out */, int* totals /* [2] out */,
+                      float* first_oct_dis /* [n_rays] out */, void* stream);
 int f2b_sampler_gather(const float* rays_d, const int* pts_idx_bounds, int n_rays,
                        const float* s_pts, const float* s_dt, const float* s_t, const int* s_anchors,
                        float* pts, float* dirs, float* dt, float* t, int* anchors, void* stream);
