@@ -75,17 +75,24 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # noqa: BLE001
             self.err = str(e)[:120]
 
-    def run(self):
+    def poll(self):
+        """One sample NOW.  The timed loops call this right after enqueueing their closing event, while the GPU still works through
+        the last step (an NVML query holds a driver lock for tens of ms on this driver: taken from the launching thread at that
+        point it cannot stall a kernel submission; the background thread below polls rarely for the same reason)."""
         if self.h is None:
             return
         import pynvml as nv
         try:
-            while not self.stop_flag:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
-                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
-                time.sleep(0.2)
+            self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                              nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
         except Exception as e:  # noqa: BLE001
             self.err = str(e)[:120]
+
+    def run(self):
+        while not self.stop_flag and self.h is not None:
+            time.sleep(2.0)
+            if not self.stop_flag:
+                self.poll()
 
     def summary(self):
         if not self.rows:
@@ -262,8 +269,12 @@ def run_ours(args):
     if world > 1:
         from f2nerf_b200.dist import install_grad_overlap, install_vote_sync
         install_vote_sync(prob["sampler"])
-        if os.environ.get("F2B_DP_OVERLAP", "1") == "1":
-            install_grad_overlap(prob["renderer"])                # table-gradient all-reduce per level slab, behind the scatter
+        # F2B_DP_OVERLAP=1: table-gradient all-reduce per level slab behind a per-slab scatter (dist.install_grad_overlap).  Measured
+        # on B200 (profiles/r02f_*, r02g_*): the four per-slab scatter launches cost +0.17 ms against the single 16-level launch,
+        # more than the overlapped all-reduce saves at N = 2 and 4 (4.64 / 4.73 vs 4.48 / 4.64 ms) — so the default is ONE
+        # all-reduce of the live 34 MB behind the single scatter launch.
+        if os.environ.get("F2B_DP_OVERLAP", "0") == "1":
+            install_grad_overlap(prob["renderer"])
     o, d, cam, gt = prob["host"]
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h_o, h_d, h_cam, h_gt = pin(o), pin(d), pin(cam), pin(gt)
@@ -277,6 +288,7 @@ def run_ours(args):
     # ---- device-resident timing (value): K steps bracketed by barrier + synchronize, CUDA events --------
     clocks = ClockSampler(local)                 # polling starts before the warm-up: the first NVML queries of a
     clocks.start()                               # process stall kernel submission for 100s of ms on this driver
+    clocks.poll()                                # (take that first, slow query here, outside every timed region)
     nxt = (d_o, d_d) if args.pipeline_march else None           # the same resident batch every step: the next rays are these
     for _ in range(args.warmup):                 # same object lifetimes as the timed loop (the caching allocator must have
         loss, res = train_step(prob, d_o, d_d, d_cam, d_gt, dist_sync, nxt)   # seen the steady-state peak before timing starts)
@@ -305,22 +317,30 @@ def run_ours(args):
             nk += res.weights.shape[0]
             w.append(round((time.perf_counter() - w0) * 1e3, 2))
         eb.record()
+        clocks.poll()                             # GPU still inside the timed region (the last step's backward is queued)
         barrier()
         return ea.elapsed_time(eb), w, ns, nk, _lib.LAUNCHES - l0
 
     # A step whose host wall time is far off the median (seen on fresh boxes: one NVML poll of the clock sampler
     # holding the driver lock for ~40 ms while the main thread launches) makes the whole K-step number a
     # measurement of that stall: such a run is rejected and the K steps are timed ONCE more; both are reported.
+    def stalled(w):
+        """A host-stall outlier on ANY rank (ranks must take the same branch: the verdict is all-reduced)."""
+        med = sorted(w)[len(w) // 2]
+        bad = max(w[1:] or w) > 1.5 * med and max(w[1:] or w) - med > 2.5
+        if world > 1:
+            t = torch.tensor([1.0 if bad else 0.0], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bad = bool(t.item() > 0)
+        return bool(bad)
+
     attempts = []
-    for _ in range(2):
+    for _ in range(3):                            # at most two re-measurements, every attempt disclosed in `timing_attempts`
         ms, walls, n_samples, n_kept, launches = timed_loop()
-        med = sorted(walls)[len(walls) // 2]
-        outlier = max(walls[1:] or walls) > 1.5 * med and max(walls[1:] or walls) - med > 2.5
+        outlier = stalled(walls)
         attempts.append({"ms_per_step": ms / args.steps, "host_wall_ms_per_step": walls, "rejected": bool(outlier)})
         if not outlier:
             break
-        if world > 1:
-            break                                 # ranks must take the same branch: no re-measure under torchrun
     # ---- per-kernel CUDA-event trace over the same steps (separate loop: event pairs around every C-ABI call) --
     _lib.TRACE = []
     for _ in range(args.steps):
@@ -354,12 +374,11 @@ def run_ours(args):
         return e2.elapsed_time(e3), w, ro, rd
 
     e2e_attempts = []
-    for _ in range(2):                                            # same host-stall rule as the resident loop: reject + re-time ONCE
+    for _ in range(3):                                            # same host-stall rule as the resident loop
         ms_e2e, e2e_walls, ro, rd = e2e_loop(ro, rd)
-        med = sorted(e2e_walls)[len(e2e_walls) // 2]
-        outlier = max(e2e_walls[1:] or e2e_walls) > 1.5 * med and max(e2e_walls[1:] or e2e_walls) - med > 2.5
+        outlier = stalled(e2e_walls)
         e2e_attempts.append({"ms_per_step": ms_e2e / args.steps, "host_wall_ms_per_step": e2e_walls, "rejected": bool(outlier)})
-        if not outlier or world > 1:
+        if not outlier:
             break
     clocks.stop_flag = True
     clocks.join(timeout=2)

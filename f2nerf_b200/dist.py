@@ -43,7 +43,7 @@ def install_grad_overlap(renderer):
 
     def hook(d_table, level_lo, local_size):
         flat = d_table.view(-1)
-        if level_lo == 12 or st["table"] is not d_table:                 # first group of this backward
+        if st["table"] is not d_table:                                   # first group of this backward (finish() clears the slot)
             st.update(hi=min(flat.numel(), 17 * local_size), works=[], table=d_table)
         lo = (level_lo + 1) * local_size if level_lo > 0 else 0
         if st["hi"] > lo:

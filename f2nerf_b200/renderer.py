@@ -587,11 +587,11 @@ class _FusedRenderFunction(torch.autograd.Function):
             ev.record(main)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                for lo in (12, 8, 4, 0):
+                for lo, nl in slab_groups():
                     for pts_j, anc_j, stride_j, s0, s1 in jobs:
                         if s1 > s0:
                             call("f2b_hash_bwd_levels", *hash_args, pts_j, anc_j, int(stride_j), int(s1 - s0), B["dfeat16"][s0:s1], 1,
-                                 float(grad_mul), B["d_table"], lo, 4, stream())
+                                 float(grad_mul), B["d_table"], lo, nl, stream())
                     slab_hook(B["d_table"], lo, int(field.local_size_))
             main.wait_stream(side)
             renderer.grad_slab_finish_()
@@ -743,10 +743,10 @@ class _RenderFunction(torch.autograd.Function):
             ev.record(main)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                for lo in (12, 8, 4, 0):
+                for lo, nl in slab_groups():
                     for pts_j, anc_j, stride_j, s0, s1 in jobs:
                         call("f2b_hash_bwd_levels", *hash_args, pts_j, anc_j, int(stride_j), int(s1 - s0), dfeat16[s0:s1], 1, float(grad_mul),
-                             d_table, lo, 4, stream())
+                             d_table, lo, nl, stream())
                     slab_hook(d_table, lo, int(field.local_size_))          # issued on the side stream: NCCL orders itself behind it
         main.wait_stream(side)
         if slab_hook is not None:
@@ -767,6 +767,14 @@ class _RenderFunction(torch.autograd.Function):
         renderer.nonfinite_flag_ = bad if prev is None else (prev | bad)      # OR: a second backward must not erase a hit
         ctx.pack = None                               # saved activations (~1 GB at 4 M samples) die with the backward, not with `res`
         return d_table, d_fparams, d_sparams, d_app, None, None, None, None, None, None, None, None, None, None
+
+
+def slab_groups():
+    """Level groups (first level, count) of the data-parallel scatter, top-down; the table-gradient slab above a group's lower
+    boundary is all-reduced behind it while the next group scatters (dist.install_grad_overlap).  F2B_DP_SLABS = 4 (default:
+    12-15 | 8-11 | 4-7 | 0-3), 2 (8-15 | 0-7: fewer launch tails, a larger exposed last slab) or 1."""
+    n = int(os.environ.get("F2B_DP_SLABS", "4"))
+    return {4: ((12, 4), (8, 4), (4, 4), (0, 4)), 2: ((8, 8), (0, 8)), 1: ((0, 16),)}.get(n, ((12, 4), (8, 4), (4, 4), (0, 4)))
 
 
 def check_backward_nan(renderer):
