@@ -23,6 +23,8 @@
 #include <ATen/cuda/CUDAEvent.h>
 #include <c10/cuda/CUDAStream.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -72,6 +74,28 @@ bool validate_weights() {
   static const bool on = [] { const char* e = getenv("F2B_VALIDATE_WEIGHTS"); return !e || atoi(e) != 0; }();
   return on;
 }
+// F2B_SHIM_PROFILE=1: host wall time spent inside Render (TRAIN / VALIDATE) and inside its backward, printed at exit — what share of
+// a trainer iteration the path is (both contain the waits for their own GPU work: Render ends behind the survivor-count read, the
+// backward behind its NaN-flag read)
+struct ShimProfile {
+  bool on = false;
+  double t_render_train = 0, t_render_val = 0, t_backward = 0;
+  long n_train = 0, n_val = 0, n_bwd = 0;
+  ShimProfile() { const char* e = getenv("F2B_SHIM_PROFILE"); on = e && atoi(e) != 0; }
+  ~ShimProfile() {
+    if (on)
+      std::printf("{\"f2b_shim_profile\": {\"render_train_s\": %.3f, \"n_render_train\": %ld, \"render_validate_s\": %.3f, "
+                  "\"n_render_validate\": %ld, \"backward_s\": %.3f, \"n_backward\": %ld}}\n",
+                  t_render_train, n_train, t_render_val, n_val, t_backward, n_bwd);
+  }
+};
+ShimProfile g_prof;
+struct ScopedTimer {
+  double* acc; long* cnt; std::chrono::steady_clock::time_point t0;
+  ScopedTimer(double* a, long* c) : acc(g_prof.on ? a : nullptr), cnt(c), t0(std::chrono::steady_clock::now()) {}
+  ~ScopedTimer() { if (acc) { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++*cnt; } }
+};
+
 bool mlp_recompute() {
   static const bool on = [] { const char* e = getenv("F2B_MLP_RECOMPUTE"); return !e || atoi(e) != 0; }();
   return on;
@@ -183,6 +207,7 @@ public:
   }
 
   static variable_list backward(AutogradContext* ctx, variable_list g) {
+    ScopedTimer prof_timer(&g_prof.t_backward, &g_prof.n_bwd);
     const int64_t pack_id = ctx->saved_data["pack"].toInt();
     std::shared_ptr<Pack> pk;
     {
@@ -266,6 +291,8 @@ public:
 // =================================================================================================================
 RenderResult Renderer::Render(const Tensor& rays_o_raw, const Tensor& rays_d_raw, const Tensor& bounds_raw, const Tensor& emb_idx) {
   if (g_use_reference) return f2b_reference_render(this, rays_o_raw, rays_d_raw, bounds_raw, emb_idx);
+  const bool prof_train = global_data_pool_->mode_ == RunningMode::TRAIN;
+  ScopedTimer prof_timer(prof_train ? &g_prof.t_render_train : &g_prof.t_render_val, prof_train ? &g_prof.n_train : &g_prof.n_val);
   auto* sampler = dynamic_cast<PersSampler*>(pts_sampler_.get());
   auto* field = dynamic_cast<Hash3DAnchored*>(scene_field_.get());
   auto* shader = dynamic_cast<SHShader*>(shader_.get());
