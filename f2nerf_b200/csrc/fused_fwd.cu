@@ -8,7 +8,7 @@
 // slots + its 128 table gathers (SURVEY.md §8d "fused forward pipeline": 512 B/pt of gathers is the whole traffic).
 //
 // Shape: a "walker" (128 threads, thread i == sample i == TMEM lane i) walks ONE RAY front to back, a 128-sample tile at a
-// time, and carries the ray's optical depth across tiles; a CTA holds two independent walkers that share the weights.  Because the reference's early-stop mask `T_i > 1e-4`
+// time, and carries the ray's optical depth across tiles; a CTA holds one walker (optionally two independent ones sharing the weights).  Because the reference's early-stop mask `T_i > 1e-4`
 // (Renderer.cpp:125) is a prefix of the ray (tau >= 0 => T non-increasing), the walk simply ENDS at the first tile whose
 // leading sample is already opaque: the samples behind it are never encoded (the unfused path encodes every marched sample,
 // then drops them).  No occupancy votes are taken in VALIDATE mode, so nothing downstream needs those samples.
@@ -95,8 +95,9 @@ __device__ __forceinline__ int walker_sync_count(int w, bool pred) {
   return n;
 }
 
-// NW = 1: the CTA is one walker (4 CTAs per SM); NW = 2: two walkers share the 20 KB of weights, so SIX walkers fit an SM (three
-// CTAs, <= 80 registers) instead of four — a walker's MLP / composite phases no longer leave the gather pipe idle as often.
+// NW = 1 (default): the CTA is one walker (4 CTAs per SM); NW = 2: two walkers share the 20 KB of weights, so SIX walkers fit an SM
+// (three CTAs, <= 80 registers) instead of four — more walkers to keep the gather pipe busy during each other's MLP / composite
+// phases, but fewer gathers in flight per thread: measured slower (see the launcher).
 template <int NW>
 __global__ void __launch_bounds__(kRT * NW, NW == 2 ? 3 : 4)
 render_fwd_fused_kernel(const __half* __restrict__ table, const int* __restrict__ prim_pool, const float* __restrict__ bias_pool,
@@ -320,8 +321,11 @@ extern "C" int f2b_render_fwd_fused(const void* table_f16, const int* prim_pool,
   int sms = 148;
   f2b_device_info(&sms, nullptr);
   if (cudaMemsetAsync(ticket, 0, sizeof(int), as_stream(stream)) != cudaSuccess) { set_error("f2b_render_fwd_fused: memset failed"); return F2B_ECUDA; }
-  static int walkers = -1;                                       // ray walkers per CTA (F2B_FUSED_WALKERS, default 2)
-  if (walkers < 0) { const char* e = getenv("F2B_FUSED_WALKERS"); walkers = (e && atoi(e) == 1) ? 1 : 2; }
+  // ray walkers per CTA (F2B_FUSED_WALKERS).  Measured on B200 (profiles/r02i_bench_w1.json / _w2.json, forward-only Render of the
+  // headline batch): one walker per CTA (4 per SM, 110 registers) 2.11 ms, two (6 per SM, 80 registers: fewer gathers in flight per
+  // thread) 2.57 ms — the default is one.
+  static int walkers = -1;
+  if (walkers < 0) { const char* e = getenv("F2B_FUSED_WALKERS"); walkers = (e && atoi(e) == 2) ? 2 : 1; }
 #define F2B_FUSED_LAUNCH(NW, PER_SM)                                                                                              \
   {                                                                                                                               \
     const int want = div_up(n_rays, NW);                                                                                          \
