@@ -90,11 +90,11 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         # An NVML query holds a driver lock for tens of ms on this driver and perturbs kernel submission for a while afterwards:
-        # the first (slowest) queries happen before the warm-up, then one every 0.5 s.  A timed loop that one of them lands in is
+        # the first (slowest) queries happen before the warm-up, then one every 0.3 s.  A timed loop that one of them lands in is
         # rejected by the host-stall rule below and re-timed (all attempts are reported).
         while not self.stop_flag and self.h is not None:
             self.poll()
-            time.sleep(0.5)
+            time.sleep(0.3)
 
     def summary(self):
         if not self.rows:
@@ -390,7 +390,7 @@ def run_ours(args):
     ms_e2e = best_e2e
     clocks.stop_flag = True
     clocks.join(timeout=2)
-    clocks_note = "polled every 0.5 s from before the warm-up; rows kept from the first timed step on"
+    clocks_note = "polled every 0.3 s from before the warm-up; rows kept from the first timed step on"
     need = torch.tensor([1.0 if (rank == 0 and not clocks.rows) else 0.0], device=device)
     if world > 1:
         dist.broadcast(need, src=0)               # every rank takes the same branch (the extra steps contain collectives)
