@@ -188,9 +188,9 @@ ALGO_BYTES = {  # algorithmic bytes per unit (sample) at the operator boundary â
 }
 
 
-NCU_KERNEL = {"f2b_hash_bwd": "hash_bwd_kernel<1>", "f2b_sampler_march": "march16_kernel<2>",
+NCU_KERNEL = {"f2b_hash_bwd": "hash_bwd_kernel<1>", "f2b_sampler_march": "march16_kernel<2, 0>",
               "f2b_field_fwd_slots": "field_fwd_kernel<1, 4>", "f2b_field_fwd": "field_fwd_kernel<1, 4>",
-              "f2b_mlp_bwd2": "mlp_bwd_tc_kernel<1>",
+              "f2b_mlp_bwd2": "mlp_bwd_rc_kernel<1>",
               "f2b_compact_slots": "compact_slots_kernel", "f2b_composite_fwd": "composite_fwd_kernel",
               "f2b_composite_bwd": "composite_bwd_kernel<0>", "f2b_composite_act_bwd": "composite_bwd_kernel<1>"}
 
