@@ -51,7 +51,7 @@ def test_clock_sampler_is_inert_on_non_sampling_ranks():
 
 def test_committed_bench_lines_carry_the_contract_keys():
     """The driver-format lines kept under profiles/ (the numbers DESIGN.md / BASELINE.md quote) have every key of the bench contract."""
-    line = json.loads(open(os.path.join(ROOT, "profiles", "r02k_bench.json")).read().strip().splitlines()[-1])
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02q_bench.json")).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
               "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in line, k
@@ -60,3 +60,5 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     ref = json.loads(open(os.path.join(ROOT, "profiles", "r02h_bench_ref.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["config"] == line["config"] and ref["metric"] == line["metric"]
+    gov = {r["kernel"]: r["governing"] for r in line["rooflines"]}
+    assert 0.9 < gov["f2b_field_fwd_slots"]["frac"] <= 1.01 and 0.6 < gov["f2b_hash_bwd"]["frac"] < 0.95
